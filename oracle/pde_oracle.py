@@ -194,7 +194,7 @@ def lp_loss(xi: torch.Tensor, mask: Sequence[bool], p: float) -> torch.Tensor:
     w = torch.zeros_like(xi.detach())
     for k in range(xi.numel()):
         if not bool(mask[k]):
-            w[k] = 1.0 / max(delta, abs(float(xi[k])) ** (2.0 - p))
+            w[k] = 1.0 / max(delta, abs(float(xi[k].detach())) ** (2.0 - p))
     return (w * xi * xi).sum()
 
 

@@ -1,0 +1,33 @@
+// plan_codegen.hpp -- host-side plan description and the code generator interface.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <functional>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace pdl_host {
+
+struct PlanSpec {
+    int d = 2;
+    std::vector<int> widths;                                 // d, hidden..., 1
+    int activation = 0;                                      // 0 tanh, 1 rational
+    int mode = 0;                                            // 0 collocation, 1 data
+    std::vector<std::array<int, 4>> encodings;               // library derivatives, padded to 4 axes
+    std::vector<std::vector<std::pair<int, int>>> terms;     // term 0 = LHS; (derivative index, power)
+    int warps_per_cta = 0;                                   // 0 = default
+};
+
+struct PlanMeta {
+    int d = 0, n_jets = 0, n_rhs = 0, hidden_layers = 0, wp = 0, max_order = 0, mode = 0, activation = 0;
+    int n_param_tensors = 0, n_param_scalars = 0, sf = 0, gs = 0, nw = 0, smem_bytes = 0;
+    long long flops_per_point = 0;
+    std::vector<std::array<int, 4>> jets;
+};
+
+uint64_t fnv1a(const std::string& s);
+int smem_floats(const PlanMeta& m, int nw);
+std::string generate_plan_source(const PlanSpec& spec, PlanMeta* meta_out);
+
+}  // namespace pdl_host

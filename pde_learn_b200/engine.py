@@ -1,0 +1,272 @@
+"""
+Host glue between torch tensors and the C ABI (libpdelearn_b200.so): plan cache, workspaces, launches and
+the torch.autograd.Function wrappers.  Everything numerical happens in the CUDA kernels; this file only
+marshals pointers and hands gradients to autograd.  There is no CPU path: tensors must live on a CUDA
+device and the native library must be built, otherwise the calls raise.
+"""
+import ctypes as C
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+_RATIONAL_NAMES = ("Rational",)
+
+
+# ----------------------------------------------------------------------------------------------
+# network introspection (works for pde_learn_b200.Network and for the reference's Network class)
+# ----------------------------------------------------------------------------------------------
+
+def network_signature(U) -> Tuple[Tuple[int, ...], int]:
+    """(widths, activation id) of a Network-like module; raises for anything the kernels cannot run."""
+    if not hasattr(U, "Layers") or not hasattr(U, "Activation_Functions"):
+        raise TypeError("U must be a Network (Layers / Activation_Functions). Arbitrary callables would need "
+                        "autograd on the CPU; this engine has no such fallback.")
+    layers = list(U.Layers)
+    widths = [int(layers[0].weight.shape[1])] + [int(l.weight.shape[0]) for l in layers]
+    acts = list(U.Activation_Functions)
+    if type(acts[-1]).__name__ != "Identity":
+        raise ValueError("output activation must be None/Identity (Code/main.py:139)")
+    names = {type(a).__name__ for a in acts[:-1]}
+    if len(names) != 1:
+        raise ValueError("hidden layers must share one activation type, got %s" % sorted(names))
+    name = names.pop()
+    if name == "Tanh":
+        act = L.PDL_ACT_TANH
+    elif name in _RATIONAL_NAMES:
+        act = L.PDL_ACT_RATIONAL
+    else:
+        raise ValueError("activation %s is not implemented in the CUDA kernels (Tanh, Rational); no fallback" % name)
+    return tuple(widths), act
+
+
+def network_param_tensors(U) -> List[torch.Tensor]:
+    """Parameter tensors in the order of list(U.parameters()) (SURVEY 'Parameter order')."""
+    out: List[torch.Tensor] = []
+    for l in U.Layers:
+        out += [l.weight, l.bias]
+    for a in list(U.Activation_Functions)[:-1]:
+        if type(a).__name__ in _RATIONAL_NAMES:
+            out += [a.a, a.b]
+    return out
+
+
+def _check_cuda_f32(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: this engine has no CPU path" % what)
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32, got %s" % (what, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# plans
+# ----------------------------------------------------------------------------------------------
+
+class Plan:
+    """One compiled kernel family: architecture + library of terms (or the data-loss residual)."""
+
+    def __init__(self, d, widths, activation, mode, encodings, terms):
+        self.desc, self._keep = L.make_desc(d, widths, activation, mode, encodings, terms)
+        h = C.c_void_p()
+        L.check(L.lib().pdl_plan_create(C.byref(self.desc), C.byref(h)))
+        self.handle = h
+        info = L.PlanInfo()
+        L.check(L.lib().pdl_plan_info_get(h, C.byref(info)))
+        self.info = info
+        self.d, self.J, self.K = int(info.d), int(info.n_jets), int(info.n_rhs_terms)
+        self.n_param_tensors, self.n_param_scalars = int(info.n_param_tensors), int(info.n_param_scalars)
+        self.flops_per_point = int(info.flops_per_point)
+        self.jets = [tuple(int(info.jet_encodings[c][a]) for a in range(4)) for c in range(self.J)]
+        self._ws: Dict[int, torch.Tensor] = {}
+        self._sm: Dict[int, int] = {}
+
+    def workspace(self, device: torch.device) -> Tuple[torch.Tensor, int]:
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if idx not in self._ws:
+            with torch.cuda.device(idx):
+                n = C.c_int32(0)
+                L.check(L.lib().pdl_device_sm_count(C.byref(n)))
+                self._sm[idx] = int(n.value)
+                nbytes = int(L.lib().pdl_plan_workspace_bytes(self.handle, self._sm[idx]))
+                self._ws[idx] = torch.empty(nbytes, dtype=torch.uint8, device=torch.device("cuda", idx))
+        return self._ws[idx], self._sm[idx]
+
+    def launch(self, points, params, xi, mask, targets, inv_n, backward, residual, features, grad_params, grad_xi,
+               stats):
+        dev = points.device
+        ws, n_sm = self.workspace(dev)
+        arr = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
+        a = L.LaunchArgs()
+        a.points = points.data_ptr(); a.n_points = int(points.shape[0])
+        a.params = arr; a.n_params = len(params)
+        a.xi = xi.data_ptr() if xi is not None else None
+        a.mask = mask.data_ptr() if mask is not None else None
+        a.targets = targets.data_ptr() if targets is not None else None
+        a.inv_n = float(inv_n); a.backward = 1 if backward else 0
+        a.residual = residual.data_ptr() if residual is not None else None
+        a.features = features.data_ptr() if features is not None else None
+        a.grad_params = grad_params.data_ptr() if grad_params is not None else None
+        a.grad_xi = grad_xi.data_ptr() if grad_xi is not None else None
+        a.stats = stats.data_ptr()
+        a.workspace = ws.data_ptr(); a.workspace_bytes = ws.numel(); a.n_ctas = n_sm
+        a.stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            L.check(L.lib().pdl_loss_launch(self.handle, C.byref(a)))
+
+
+_PLANS: Dict[tuple, Plan] = {}
+
+
+def _enc_tuple(D) -> Tuple[int, ...]:
+    return tuple(int(v) for v in np.asarray(D.Encoding).tolist())
+
+
+def library_key(Derivatives, LHS_Term, RHS_Terms):
+    """Hashable description of the library: distinct encodings + (encoding index, power) lists, LHS first."""
+    encs: List[Tuple[int, ...]] = []
+
+    def idx(D):
+        e = _enc_tuple(D)
+        e = e + (0,) * (4 - len(e))
+        if e not in encs:
+            encs.append(e)
+        return encs.index(e)
+
+    for D in Derivatives:
+        idx(D)
+    terms = []
+    for T in [LHS_Term] + list(RHS_Terms):
+        terms.append(tuple((idx(D), int(p)) for D, p in zip(T.Derivatives, T.Powers)))
+    return tuple(encs), tuple(terms)
+
+
+def collocation_plan(U, Derivatives, LHS_Term, RHS_Terms) -> Plan:
+    widths, act = network_signature(U)
+    encs, terms = library_key(Derivatives, LHS_Term, RHS_Terms)
+    key = (widths, act, L.PDL_MODE_COLLOCATION, encs, terms)
+    if key not in _PLANS:
+        _PLANS[key] = Plan(widths[0], widths, act, L.PDL_MODE_COLLOCATION, encs, [list(t) for t in terms])
+    return _PLANS[key]
+
+
+def data_plan(U) -> Plan:
+    widths, act = network_signature(U)
+    key = (widths, act, L.PDL_MODE_DATA)
+    if key not in _PLANS:
+        _PLANS[key] = Plan(widths[0], widths, act, L.PDL_MODE_DATA, [(0, 0, 0, 0)], [[(0, 1)]])
+    return _PLANS[key]
+
+
+# ----------------------------------------------------------------------------------------------
+# mask cache (the reference keeps Mask as a CPU bool tensor; the kernels want a device byte array)
+# ----------------------------------------------------------------------------------------------
+_MASKS: Dict[tuple, torch.Tensor] = {}
+
+
+def device_mask(Mask, K: int, device: torch.device) -> torch.Tensor:
+    if isinstance(Mask, torch.Tensor) and Mask.is_cuda:
+        return Mask.to(torch.uint8).contiguous()
+    m = np.asarray(Mask.detach().cpu().numpy() if isinstance(Mask, torch.Tensor) else Mask).astype(np.uint8).reshape(-1)
+    assert m.size == K, "Mask must have one entry per RHS term"
+    key = (m.tobytes(), device.index)
+    if key not in _MASKS:
+        _MASKS[key] = torch.from_numpy(m.copy()).to(device)
+    return _MASKS[key]
+
+
+# ----------------------------------------------------------------------------------------------
+# autograd wrappers: loss and every gradient come out of ONE fused launch; backward only rescales
+# ----------------------------------------------------------------------------------------------
+
+def _split_flat(flat: torch.Tensor, shapes) -> List[torch.Tensor]:
+    out, off = [], 0
+    for shp in shapes:
+        n = int(np.prod(shp))
+        out.append(flat[off:off + n].view(shp))
+        off += n
+    return out
+
+
+class _CollLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan: Plan, points, mask_dev, inv_n, want_grad, xi, *params):
+        dev = points.device
+        n = points.shape[0]
+        residual = torch.empty(n, dtype=torch.float32, device=dev)
+        stats = torch.empty(4, dtype=torch.float64, device=dev)
+        gp = gx = None
+        if want_grad:
+            gp = torch.empty(plan.n_param_scalars, dtype=torch.float32, device=dev)
+            gx = torch.empty(max(plan.K, 1), dtype=torch.float32, device=dev)
+        plan.launch(points, params, xi, mask_dev, None, inv_n, want_grad, residual, None, gp, gx, stats)
+        ctx.gp, ctx.gx, ctx.n_params, ctx.K = gp, gx, len(params), plan.K
+        ctx.shapes = [p.shape for p in params]
+        ctx.mark_non_differentiable(residual)
+        return stats[0].to(torch.float32), residual
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_res):
+        if ctx.gp is None:
+            raise RuntimeError("Coll_Loss was evaluated without gradients")
+        grads = _split_flat(ctx.gp * g_loss, ctx.shapes)
+        return (None, None, None, None, None, ctx.gx[:ctx.K] * g_loss, *grads)
+
+
+class _DataLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan: Plan, inputs, targets, inv_n, want_grad, *params):
+        dev = inputs.device
+        stats = torch.empty(4, dtype=torch.float64, device=dev)
+        gp = torch.empty(plan.n_param_scalars, dtype=torch.float32, device=dev) if want_grad else None
+        plan.launch(inputs, params, None, None, targets, inv_n, want_grad, None, None, gp, None, stats)
+        ctx.gp = gp
+        ctx.shapes = [p.shape for p in params]
+        return stats[0].clone()                       # float64, like the reference (f32 prediction - f64 target)
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        if ctx.gp is None:
+            raise RuntimeError("Data_Loss was evaluated without gradients")
+        grads = _split_flat(ctx.gp * g_loss.to(torch.float32), ctx.shapes)
+        return (None, None, None, None, None, *grads)
+
+
+class _LpLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xi, mask_dev, p):
+        out = torch.empty(1, dtype=torch.float32, device=xi.device)
+        grad = torch.empty_like(xi)
+        with torch.cuda.device(xi.device):
+            L.check(L.lib().pdl_lp_loss(xi.data_ptr(), mask_dev.data_ptr(), int(xi.numel()), float(p), out.data_ptr(),
+                                        grad.data_ptr(), torch.cuda.current_stream(xi.device).cuda_stream))
+        ctx.grad = grad
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.grad * g, None, None
+
+
+class _L2LossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, *params):
+        dev = params[0].device
+        n = len(params)
+        ptrs = (C.c_void_p * n)(*[p.data_ptr() for p in params])
+        sizes = (C.c_int32 * n)(*[int(p.numel()) for p in params])
+        total = sum(int(p.numel()) for p in params)
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        grad = torch.empty(total, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            L.check(L.lib().pdl_l2_squared_loss(ptrs, sizes, n, out.data_ptr(), grad.data_ptr(),
+                                                torch.cuda.current_stream(dev).cuda_stream))
+        ctx.grad = grad
+        ctx.shapes = [p.shape for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return tuple(_split_flat(ctx.grad * g, ctx.shapes))

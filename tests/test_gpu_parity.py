@@ -1,0 +1,297 @@
+"""
+GPU parity tests (run with -m gpu on a B200).  Everything goes through the public package, i.e. through the
+C ABI of libpdelearn_b200.so, and is compared with
+  * the golden vectors produced by the unmodified reference in float64 (tests/golden/*.npz), and
+  * the CPU oracle (oracle/pde_oracle.py) on seeded inputs.
+Tolerance (BASELINE.json north_star / SURVEY 8d): relative max-norm error <= 1e-5 for FP32 kernels
+against the float64 reference path; masked Xi gradients exactly 0.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pde_oracle as O
+from tests.helpers import GOLDEN_CASES, GOLDEN_DIR, GoldenCase, rel_max
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+def _network_from_golden(g, P):
+    act = "Rational" if g.activation == "rational" else "Tanh"
+    U = P.Network(Widths=g.widths, Hidden_Activation=act, Device=_dev())
+    with torch.no_grad():
+        for prm, val in zip(U.parameters(), g.params):
+            prm.copy_(val.to(_dev()))
+    return U
+
+
+def _terms(P, lhs, rhs):
+    mk = lambda t: P.Term([P.Derivative(np.array(e)) for e, _ in t], [p for _, p in t])
+    encs = O.distinct_encodings(lhs, rhs)
+    return [P.Derivative(np.array(e)) for e in encs], mk(lhs), [mk(t) for t in rhs]
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_coll_loss_and_gradients_vs_reference_golden(name):
+    import pde_learn_b200 as P
+    g = GoldenCase(name)
+    U = _network_from_golden(g, P)
+    derivs, lhs, rhs = _terms(P, g.lhs, g.rhs)
+    xi = g.xi.to(_dev()).requires_grad_(True)
+    mask = torch.tensor(g.mask, dtype=torch.bool)
+    pts = g.points.to(_dev())
+    loss, resid = P.Coll_Loss(U, xi, mask, pts, derivs, lhs, rhs)
+    assert loss.dtype == torch.float32 and loss.dim() == 0 and resid.shape == (pts.shape[0],)
+    loss.backward()
+    want = float(g.z["coll_loss"])
+    assert abs(float(loss) - want) <= TOL * abs(want)
+    assert rel_max(resid.cpu().numpy(), g.z["residual"]) <= TOL
+    got = np.concatenate([p.grad.cpu().numpy().ravel() for p in U.parameters()])
+    ref = np.concatenate([x.numpy().ravel() for x in g.grads])
+    assert rel_max(got, ref) <= TOL
+    assert rel_max(xi.grad.cpu().numpy(), g.z["grad_xi"]) <= TOL
+    for k, m in enumerate(g.mask):
+        if m:
+            assert float(xi.grad[k]) == 0.0
+    # derivative features (the reference's Derivative_From_Derivative outputs)
+    feats = P.Evaluate_Derivatives(U, derivs, pts).cpu().numpy()
+    for j in range(len(derivs)):
+        assert rel_max(feats[j], g.z["features"][j]) <= TOL, derivs[j]
+
+
+@pytest.mark.parametrize("name", ["burgers_tanh", "heat_rational", "rd2d_tanh", "wave_mixed_tanh", "burgers_rational20"])
+def test_data_lp_l2_vs_reference_golden(name):
+    import pde_learn_b200 as P
+    g = GoldenCase(name)
+    U = _network_from_golden(g, P)
+    d = P.Data_Loss(U, g.x_data.to(_dev()), g.y_data.to(_dev()))
+    assert d.dtype == torch.float64
+    d.backward()
+    assert abs(float(d) - float(g.z["data_loss"])) <= TOL * float(g.z["data_loss"])
+    got = np.concatenate([p.grad.cpu().numpy().ravel() for p in U.parameters()])
+    ref = np.concatenate([x.numpy().ravel() for x in g.dgrads])
+    assert rel_max(got, ref) <= TOL
+    xi = g.xi.to(_dev()).requires_grad_(True)
+    lp = P.Lp_Loss(xi, torch.tensor(g.mask), g.p)
+    lp.backward()
+    assert abs(float(lp) - float(g.z["lp_loss"])) <= TOL * float(g.z["lp_loss"])
+    assert rel_max(xi.grad.cpu().numpy(), g.z["lp_grad"]) <= TOL
+    for prm in U.parameters():
+        prm.grad = None
+    l2 = P.L2_Squared_Loss(U)
+    assert l2.shape == (1,) and l2.dtype == torch.float32
+    l2.backward()
+    assert abs(float(l2) - float(g.z["l2_loss"])) <= TOL * float(g.z["l2_loss"])
+    for prm in U.parameters():
+        assert torch.allclose(prm.grad, 2 * prm.detach(), rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("cfg,act,n", [("burgers", "Tanh", 10_000), ("heat", "Rational", 4099), ("ks", "Tanh", 3001),
+                                       ("rd2d", "Tanh", 2050), ("kdv", "Rational", 1025)])
+def test_configs_vs_oracle(cfg, act, n):
+    """BASELINE configs (5x40) on seeded points in the real bounds, CUDA vs float64 oracle."""
+    import pde_learn_b200 as P
+    from pde_learn_b200 import configs
+    torch.manual_seed(3)
+    d, bounds, derivs, lhs, rhs = configs.config(cfg)
+    U = P.Network([d] + [40] * 5 + [1], act, Device=_dev())
+    K = len(rhs)
+    xi = (0.1 * torch.randn(K)).to(_dev()).requires_grad_(True)
+    mask = torch.zeros(K, dtype=torch.bool); mask[K // 2] = True
+    pts = P.Generate_Points(bounds, n, _dev(), Seed=5)
+    loss, resid = P.Coll_Loss(U, xi, mask, pts, derivs, lhs, rhs)
+    loss.backward()
+    od, olhs, orhs, _ = O.config_library(cfg)
+    nl = len(U.Layers)
+    ra = [a.a.detach().cpu() for a in list(U.Activation_Functions)[:-1]] if act == "Rational" else []
+    rb = [a.b.detach().cpu() for a in list(U.Activation_Functions)[:-1]] if act == "Rational" else []
+    net = O.NetParams([l.weight.detach().cpu() for l in U.Layers], [l.bias.detach().cpu() for l in U.Layers],
+                      act.lower(), ra, rb).to(torch.float64, True)
+    xi64 = xi.detach().cpu().double().requires_grad_(True)
+    ol, orr, _ = O.coll_loss(lambda X: O.mlp_forward(net, X), xi64, mask.tolist(), pts.cpu().double(), olhs, orhs)
+    og = torch.autograd.grad(ol, net.tensors() + [xi64])
+    assert abs(float(loss) - float(ol)) <= TOL * abs(float(ol))
+    assert rel_max(resid.cpu().numpy(), orr.detach().numpy()) <= TOL
+    got = np.concatenate([p.grad.cpu().numpy().ravel() for p in U.parameters()])
+    ref = np.concatenate([x.numpy().ravel() for x in og[:-1]])
+    assert rel_max(got, ref) <= TOL
+    assert rel_max(xi.grad.cpu().numpy(), og[-1].numpy()) <= TOL
+    assert float(xi.grad[K // 2]) == 0.0
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 63, 257])
+def test_ragged_sizes(n):
+    import pde_learn_b200 as P
+    g = GoldenCase("heat_tanh")
+    U = _network_from_golden(g, P)
+    derivs, lhs, rhs = _terms(P, g.lhs, g.rhs)
+    xi = g.xi.to(_dev()).requires_grad_(True)
+    pts = g.points[:1].repeat(n, 1).to(_dev()) if n > g.points.shape[0] else g.points[:n].to(_dev())
+    loss, resid = P.Coll_Loss(U, xi, torch.tensor(g.mask), pts, derivs, lhs, rhs)
+    loss.backward()
+    want_r = g.z["residual"][:1].repeat(n) if n > g.points.shape[0] else g.z["residual"][:n]
+    assert rel_max(resid.cpu().numpy(), want_r) <= TOL
+    assert abs(float(loss) - float(np.mean(want_r ** 2))) <= TOL * float(np.mean(want_r ** 2))
+    assert all(torch.isfinite(p.grad).all() for p in U.parameters())
+
+
+def test_full_size_properties_heat_1m():
+    """Config 2 at its full size (2^20 rows): properties that do not need the oracle."""
+    import pde_learn_b200 as P
+    from pde_learn_b200 import configs
+    torch.manual_seed(0)
+    d, bounds, derivs, lhs, rhs = configs.config("heat")
+    U = P.Network([d] + [40] * 5 + [1], "Tanh", Device=_dev())
+    K = len(rhs)
+    xi = (0.1 * torch.randn(K)).to(_dev()).requires_grad_(True)
+    mask = torch.zeros(K, dtype=torch.bool)
+    N = 1 << 20
+    pts = P.Generate_Points(bounds, N, _dev(), Seed=9)
+    # (1) shards drawn with First_Index are exactly the rows of the whole batch
+    half = P.Generate_Points(bounds, N // 2, _dev(), Seed=9, First_Index=N // 2)
+    assert torch.equal(half, pts[N // 2:])
+    assert float(pts[:, 0].min()) >= bounds[0, 0] and float(pts[:, 0].max()) <= bounds[0, 1]
+    assert float(pts[:, 1].min()) >= bounds[1, 0] and float(pts[:, 1].max()) <= bounds[1, 1]
+    assert abs(float(pts[:, 1].mean()) - 5.0) < 0.02 and abs(float(pts[:, 1].var()) - 100.0 / 12.0) < 0.05
+
+    def run(p, inv_n):
+        for q in U.parameters():
+            q.grad = None
+        xi.grad = None
+        l, r = P.Coll_Loss(U, xi, mask, p, derivs, lhs, rhs, Inv_N=inv_n)
+        l.backward()
+        return float(l), r, torch.cat([q.grad.reshape(-1) for q in U.parameters()] + [xi.grad])
+
+    l_all, r_all, g_all = run(pts, 1.0 / N)
+    # (2) determinism: a second launch is bit-identical
+    l_again, r_again, g_again = run(pts, 1.0 / N)
+    assert l_all == l_again and torch.equal(r_all, r_again) and torch.equal(g_all, g_again)
+    # (3) additivity over shards (what the multi-GPU path relies on): sum of shard losses/gradients == whole
+    l_a, r_a, g_a = run(pts[:N // 2], 1.0 / N)
+    l_b, r_b, g_b = run(pts[N // 2:], 1.0 / N)
+    assert abs((l_a + l_b) - l_all) <= 2e-6 * abs(l_all)
+    assert torch.equal(torch.cat([r_a, r_b]), r_all)
+    assert float((g_a + g_b - g_all).abs().max()) <= 2e-6 * float(g_all.abs().max())
+    # (4) the loss is the mean of the squared residual it returned
+    assert abs(l_all - float((r_all.double() ** 2).mean())) <= 1e-6 * abs(l_all)
+    # (5) residual is linear in xi: r(xi) - r(0) == -(L xi) and r is affine => midpoint rule
+    with torch.no_grad():
+        z = torch.zeros_like(xi)
+        r0 = P.Coll_Loss(U, z, mask, pts[:4096], derivs, lhs, rhs)[1]
+        r1 = P.Coll_Loss(U, xi, mask, pts[:4096], derivs, lhs, rhs)[1]
+        rh = P.Coll_Loss(U, 0.5 * xi, mask, pts[:4096], derivs, lhs, rhs)[1]
+    assert float((0.5 * (r0 + r1) - rh).abs().max()) <= 1e-5 * float(r1.abs().max())
+
+
+def test_training_step_vs_reference_golden():
+    """One Adam step of Training() (two data sets sharing Xi, one masked term) vs the reference's own step."""
+    import pde_learn_b200 as P
+    z = np.load(os.path.join(GOLDEN_DIR, "training_step_heat.npz"))
+    s = json.loads(str(z["spec"]))
+    fix = lambda t: [(tuple(e), int(p)) for e, p in t]
+    derivs, lhs, rhs = _terms(P, fix(s["lhs"]), [fix(t) for t in s["rhs"]])
+    nprm = int(z["n_params"])
+    U_List = []
+    for i in range(2):
+        U = P.Network([int(w) for w in z["widths"]], "Tanh", Device=_dev())
+        with torch.no_grad():
+            for j, prm in enumerate(U.parameters()):
+                prm.copy_(torch.from_numpy(z["p0_%d_%02d" % (i, j)].copy()).to(_dev()))
+        U_List.append(U)
+    Xi = torch.from_numpy(z["xi0"].copy()).to(_dev()).requires_grad_(True)
+    Mask = torch.from_numpy(z["mask"].copy())
+    W = json.loads(str(z["weights"]))
+    coll = [torch.from_numpy(z["coll_%d" % i].copy()).to(_dev()) for i in range(2)]
+    inp = [torch.from_numpy(z["inp_%d" % i].copy()).to(_dev()) for i in range(2)]
+    tgt = [torch.from_numpy(z["tgt_%d" % i].copy()).to(_dev()) for i in range(2)]
+    te = P.Testing(U_List, Xi, Mask, coll, inp, tgt, derivs, lhs, rhs, float(z["p"]), W)
+    for key in ("Coll Losses", "Data Losses", "L2 Losses", "Total Losses"):
+        assert np.allclose(te[key], z["test_" + key.replace(" ", "_")], rtol=2e-5), key
+    assert abs(te["Lp Loss"] - float(z["test_Lp_Loss"])) <= 2e-5 * float(z["test_Lp_Loss"])
+    opt = torch.optim.Adam([q for U in U_List for q in U.parameters()] + [Xi], lr=float(z["lr"]))
+    tr = P.Training(U_List, Xi, Mask, coll, inp, tgt, derivs, lhs, rhs, float(z["p"]), W, opt)
+    for key in ("Coll Losses", "Data Losses", "L2 Losses", "Total Losses"):
+        assert np.allclose(tr[key], z["train_" + key.replace(" ", "_")], rtol=2e-5), key
+    assert abs(tr["Lp Loss"] - float(z["test_Lp_Loss"])) <= 2e-5 * float(z["test_Lp_Loss"])
+    for i in range(2):
+        assert tr["Residuals"][i].device.type == "cpu"
+        assert rel_max(tr["Residuals"][i].numpy(), z["resid_%d" % i]) <= 5e-5
+        for j, prm in enumerate(U_List[i].parameters()):
+            # Adam's first step is lr*g/(|g|+eps): entries with |g| ~ eps are ill-conditioned, so compare
+            # at 2% of the step size (lr = 1e-3)
+            assert float((prm.detach().cpu() - torch.from_numpy(z["p1_%d_%02d" % (i, j)])).abs().max()) <= 2e-5
+    assert float((Xi.detach().cpu() - torch.from_numpy(z["xi1"])).abs().max()) <= 2e-5
+    assert float(Xi[3]) == float(z["xi0"][3])          # masked component untouched
+
+
+def test_targeted_points_and_moments():
+    import ctypes as C
+    import pde_learn_b200 as P
+    from pde_learn_b200 import _lib as L
+    torch.manual_seed(1)
+    n, n_rand = 300_003, 250_000
+    pts = torch.rand(n, 2, device=_dev())
+    r = torch.randn(n, device=_dev())
+    r[17] = 11.0; r[n - 1] = -13.0
+    st = torch.zeros(2, dtype=torch.float64, device=_dev())
+    s = torch.cuda.current_stream().cuda_stream
+    L.check(L.lib().pdl_abs_residual_moments(r.data_ptr(), n_rand, st.data_ptr(), s))
+    a = r[:n_rand].abs().double()
+    assert abs(float(st[0]) - float(a.sum())) <= 1e-9 * float(a.sum())
+    assert abs(float(st[1]) - float((a * a).sum())) <= 1e-9 * float((a * a).sum())
+    cutoff, want = O.targeted_cutoff_select(pts.cpu(), r.cpu(), n_rand)
+    out = torch.empty_like(pts); cnt = torch.zeros(1, dtype=torch.int64, device=_dev())
+    scratch = torch.empty((n + 1023) // 1024 + 1, dtype=torch.int32, device=_dev())
+    L.check(L.lib().pdl_select_targeted(pts.data_ptr(), r.data_ptr(), n, 2, C.c_float(cutoff), out.data_ptr(),
+                                        cnt.data_ptr(), scratch.data_ptr(), s))
+    k = int(cnt[0])
+    assert k == want.shape[0]
+    assert torch.equal(out[:k].cpu(), want)            # same rows, same order (bit-exact index work)
+
+
+def test_adam_matches_torch():
+    from pde_learn_b200 import _lib as L
+    torch.manual_seed(2)
+    n = 6750
+    th = torch.randn(n, device=_dev()); ref = th.clone().requires_grad_(True)
+    m = torch.zeros(n, device=_dev()); v = torch.zeros(n, device=_dev())
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    for step in range(1, 6):
+        g = torch.randn(n, device=_dev())
+        ref.grad = g.clone(); opt.step()
+        L.check(L.lib().pdl_adam_step(th.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8,
+                                      step, torch.cuda.current_stream().cuda_stream))
+    assert float((th - ref.detach()).abs().max()) <= 2e-6
+
+
+def test_lp_closed_forms():
+    """Known answers of the reference's Lp test (Test/Test_Loss.py:180-223)."""
+    import pde_learn_b200 as P
+    N, p, x = 37, 0.07, 0.043
+    mask = torch.zeros(N, dtype=torch.bool)
+    assert abs(float(P.Lp_Loss(torch.zeros(N, device=_dev()), mask, p))) < 1e-5
+    xi = torch.full((N,), x, device=_dev())
+    assert abs(float(P.Lp_Loss(xi, mask, p)) - N * x ** p) < 1e-4
+    xi[11:] = 0
+    assert abs(float(P.Lp_Loss(xi, mask, p)) - 11 * x ** p) < 1e-4
+    with pytest.raises(AssertionError):
+        P.Lp_Loss(xi, mask, 2.5)
+
+
+def test_no_cpu_fallback():
+    import pde_learn_b200 as P
+    g = GoldenCase("heat_tanh")
+    derivs, lhs, rhs = _terms(P, g.lhs, g.rhs)
+    U = P.Network(g.widths, "Tanh")                     # CPU network
+    with pytest.raises(RuntimeError):
+        P.Coll_Loss(U, g.xi, torch.tensor(g.mask), g.points, derivs, lhs, rhs)
+    with pytest.raises(TypeError):                      # a bare callable (reference tests use polynomials) is refused
+        P.Coll_Loss(lambda X: X.sum(1), g.xi.to(_dev()), torch.tensor(g.mask), g.points.to(_dev()), derivs, lhs, rhs)
