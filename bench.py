@@ -120,41 +120,63 @@ def workload_name(w, act):
 # ------------------------------------------------------------------------------------------------------
 
 class ClockSampler:
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
-        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """Samples SM clock, power and throttle reasons of one GPU through NVML every ~5 ms while a region runs."""
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.rows, self._stop, self._thr, self.err = index, [], threading.Event(), None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
+            import pynvml as N
+            N.nvmlInit()
+            self.N = N
+            uuid = None
             try:
-                sm.append(float(r[1])); mx = float(r[2])
-                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
-                    if r[col].lower().startswith("active"):
-                        reasons.add(name)
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
             except Exception:
                 pass
-        sm.sort()
-        load = sm[len(sm) // 2:] if sm else []
-        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+            self.h = None
+            if uuid:
+                try:
+                    self.h = N.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+                except Exception:
+                    self.h = None
+            if self.h is None:
+                self.h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM)
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        except Exception as e:                      # noqa: BLE001
+            self.err = repr(e)
+
+    def _run(self):
+        N = self.N
+        while not self._stop.is_set():
+            try:
+                sm = N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)
+                pw = N.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = N.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.rows.append((sm, pw, rs))
+            except Exception as e:                  # noqa: BLE001
+                self.err = repr(e)
+                return
+            time.sleep(0.005)
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=1.0)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples: %s" % self.err], "samples": 0}
+        N = self.N
+        names = {"hw_slowdown": N.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": N.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": N.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": N.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(k for k, bit in names.items() if any(r[2] & bit for r in self.rows))
+        pmax = max(r[1] for r in self.rows)
+        load = [r[0] for r in self.rows if r[1] >= 0.6 * pmax] or [r[0] for r in self.rows]
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "power_w_max": pmax, "samples": len(self.rows)}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -230,10 +252,11 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-timed steps, inputs resident in HBM ----
+    sampler = ClockSampler(local); sampler.start()
     for _ in range(args.warmup):
         closure(coll)
     barrier()
-    sampler = ClockSampler(local); sampler.start()
+    sampler.rows.clear()                               # keep only samples taken during the timed region
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for i in range(args.steps):
         flush.zero_()                                   # evict L2 between timed iterations (inputs are 8 MB)
@@ -298,7 +321,7 @@ def run_ours(args):
         for i in range(S):
             dev_pts[i].copy_(host_pts[i], non_blocking=True)
         total = closure(dev_pts)
-        return float(total)                              # device -> host read of the step's result
+        return float(total.detach())                     # device -> host read of the step's result
 
     for _ in range(max(3, args.warmup // 2)):
         e2e_step()

@@ -36,6 +36,8 @@ def _parse_sub_term(text: str) -> Tuple[Derivative, int]:
         if "^" in body:
             body, o = body.split("^", 1)
             order = int(o)
+        if body.lower() not in _AXIS:
+            raise ValueError("unknown differentiation variable %r in %r" % (body, text))
         enc[_AXIS[body.lower()]] += order
     n = 4
     while n > 2 and enc[n - 1] == 0:

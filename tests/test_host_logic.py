@@ -1,0 +1,113 @@
+"""Host-side logic that needs no GPU: symbols, Library.txt reader, configs, network introspection, gloo all-reduce."""
+import json
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+import pde_learn_b200 as P
+from pde_learn_b200 import configs, engine
+from pde_learn_b200.Library_Reader import Parse_Term, Read_Library
+from tests.helpers import GOLDEN_DIR
+
+SHIPPED = configs.SHIPPED_LIBRARY
+
+
+def test_read_library_matches_reference_reader():
+    with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
+        f.write("# comment line\n\n" + SHIPPED.replace("(U)^2\n", "(U)^2   # trailing comment\n", 1))
+        path = f.name
+    derivs, lhs, rhs = Read_Library(path)
+    os.unlink(path)
+    blob = json.load(open(os.path.join(GOLDEN_DIR, "library_txt_parsed.json")))
+    st = lambda T: [[[int(v) for v in D.Encoding], int(p)] for D, p in zip(T.Derivatives, T.Powers)]
+    assert [[int(v) for v in D.Encoding] for D in derivs] == blob["derivatives"]
+    assert st(lhs) == blob["lhs"] and [st(t) for t in rhs] == blob["rhs"]
+
+
+def test_parse_term_grammar():
+    T = Parse_Term("(D_x^2 D_y U)^3*(D_t U)*U^2")
+    assert [D.Encoding.tolist() for D in T.Derivatives] == [[0, 2, 1], [1, 0], [0, 0]]
+    assert T.Powers == [3, 1, 2] and T.Num_Sub_Terms == 3
+    assert str(P.Derivative(np.array([1, 2, 0, 1]))) == "D_t D_x^2 D_z "
+    with pytest.raises(ValueError):
+        Parse_Term("(D_q U)")
+
+
+def test_derivative_and_term_semantics():
+    a, b = P.Derivative(np.array([0, 1])), P.Derivative(np.array([0, 2]))
+    assert a.Order == 1 and a.Is_Child_Of(b) and not b.Is_Child_Of(a)
+    with pytest.raises(AssertionError):
+        P.Derivative(np.array([1]))
+    with pytest.raises(AssertionError):
+        P.Term([a], [0])
+    t = P.Term([a, b], [1, 2])
+    t2 = P.Build_Term_From_State(t.Get_State())
+    assert str(t2) == str(t) == "(D_x U)*(D_x^2 U)^2"
+
+
+def test_config_sizes_match_survey():
+    for name, J, K, d in [("burgers", 5, 17, 2), ("heat", 4, 9, 2), ("kdv", 5, 14, 2), ("ks", 6, 30, 2), ("rd2d", 6, 21, 3)]:
+        dd, bounds, derivs, lhs, rhs = configs.config(name)
+        assert (dd, len(derivs), len(rhs), bounds.shape) == (d, J, K, (d, 2))
+
+
+def test_network_layout_and_signature():
+    torch.manual_seed(0)
+    U = P.Network([2, 40, 40, 40, 40, 40, 1], "Rational")
+    names = [n for n, _ in U.named_parameters()]
+    assert names[:4] == ["Layers.0.weight", "Layers.0.bias", "Layers.1.weight", "Layers.1.bias"]
+    assert names[-2:] == ["Activation_Functions.4.a", "Activation_Functions.4.b"]
+    assert sum(p.numel() for p in U.parameters()) == 6721 + 35          # SURVEY "Parameter order"
+    assert [tuple(p.shape) for p in engine.network_param_tensors(U)] == [tuple(p.shape) for p in U.parameters()]
+    assert engine.network_signature(U) == ((2, 40, 40, 40, 40, 40, 1), 1)
+    assert float(U.Layers[0].bias.detach().abs().max()) == 0.0
+    V = P.Network([2, 40, 40, 40, 40, 40, 1], "Rational")
+    V.Set_State(U.Get_State())
+    x = torch.rand(5, 2)
+    assert torch.equal(U(x), V(x))
+    with pytest.raises(ValueError):
+        engine.network_signature(P.Network([2, 8, 1], "Sigmoid"))
+    with pytest.raises(TypeError):
+        engine.network_signature(lambda X: X)
+    with pytest.raises(ValueError):
+        P.Network([2, 8, 1], "Sin")                     # accepted by the reference's reader, not by its Network
+
+
+def test_library_key_pads_and_dedups():
+    d, _, derivs, lhs, rhs = configs.config("rd2d")
+    encs, terms = engine.library_key(derivs, lhs, rhs)
+    assert (0, 0, 1, 0) in encs and (0, 0, 0, 0) in encs and len(encs) == 6
+    assert terms[0] == ((encs.index((1, 0, 0, 0)), 1),) and len(terms) == 22
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pde_learn_b200.Test_Train import _global_counts, allreduce_gradients
+    a = torch.nn.Parameter(torch.zeros(3, 2)); b = torch.nn.Parameter(torch.zeros(5)); c = torch.nn.Parameter(torch.zeros(1))
+    a.grad = torch.full((3, 2), float(rank + 1)); b.grad = torch.arange(5.0) * (rank + 1)     # c.grad stays None
+    allreduce_gradients([a, b, c], dist.group.WORLD)
+    counts = _global_counts([100 + rank, 7], dist.group.WORLD)
+    q.put((rank, a.grad.clone(), b.grad.clone(), c.grad, counts))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ga, gb, gc, counts in got:
+        assert torch.equal(ga, torch.full((3, 2), 3.0))
+        assert torch.equal(gb, torch.arange(5.0) * 3)
+        assert gc is None and counts == [201, 14]
