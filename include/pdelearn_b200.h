@@ -126,6 +126,11 @@ int pdl_sample_points(const double* bounds, int32_t d, int64_t n, uint64_t seed,
 int pdl_abs_residual_moments(const float* residual, int64_t n_random, double* stats, void* stream);
 int pdl_select_targeted(const float* points, const float* residual, int64_t n, int32_t d, float cutoff,
                         float* out_points, int64_t* out_count, int32_t* block_scratch, void* stream);
+/* The whole update without a host round trip: moments over the first n_random rows, cutoff = mean + 3*std
+ * (unbiased) computed on the device, then the compaction.  stats: device double[4] (sum|r|, sum r^2, cutoff as
+ * float in stats[2], reserved). */
+int pdl_targeted_update(const float* points, const float* residual, int64_t n, int64_t n_random, int32_t d,
+                        float* out_points, int64_t* out_count, double* stats, int32_t* block_scratch, void* stream);
 
 /* Fused Adam update over a flat parameter vector (torch.optim.Adam semantics, no weight decay / amsgrad):
  * the optimiser step of Code/Test_Train.py:193 for the Adam branch of Code/main.py:232-246. */

@@ -58,6 +58,8 @@ PROTOTYPES = {
     "pdl_abs_residual_moments": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pdl_select_targeted": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pdl_targeted_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdl_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
                                 C.c_double, C.c_double, C.c_double, C.c_int64, C.c_void_p]),
     "pdl_measure_fp32_peak": (C.c_int, [C.POINTER(C.c_double), C.c_void_p]),

@@ -341,7 +341,17 @@ __global__ void moments_kernel(const float* __restrict__ r, long long n, double*
         atomicAdd(&stats[0], a); atomicAdd(&stats[1], b);
     }
 }
-__global__ void select_count_kernel(const float* __restrict__ r, long long n, float cutoff, int* __restrict__ counts) {
+__global__ void cutoff_kernel(const double* __restrict__ stats, long long n_random, float* __restrict__ out) {
+    // mean + 3 * unbiased std of |r| over the random rows (Code/main.py:369-380)
+    const double n = (double)n_random;
+    const double mean = n > 0 ? stats[0] / n : 0.0;
+    double var = n > 1 ? (stats[1] - n * mean * mean) / (n - 1.0) : 0.0;
+    if (var < 0.0) var = 0.0;
+    out[0] = (float)(mean + 3.0 * sqrt(var));
+}
+__global__ void select_count_kernel(const float* __restrict__ r, long long n, float cutoff, const float* __restrict__ cutoff_dev,
+                                    int* __restrict__ counts) {
+    if (cutoff_dev) cutoff = cutoff_dev[0];
     const long long i = (long long)blockIdx.x * 1024 + threadIdx.x;
     const int flag = (i < n && fabsf(r[i]) >= cutoff) ? 1 : 0;
     const int c = __syncthreads_count(flag);
@@ -376,8 +386,9 @@ __global__ void select_scan_kernel(int* __restrict__ counts, int n_blocks, long 
     if (threadIdx.x == 0) *total = carry;
 }
 __global__ void select_scatter_kernel(const float* __restrict__ pts, const float* __restrict__ r, long long n, int d, float cutoff,
-                                      const int* __restrict__ offsets, float* __restrict__ out) {
+                                      const float* __restrict__ cutoff_dev, const int* __restrict__ offsets, float* __restrict__ out) {
     __shared__ int wsum[32];
+    if (cutoff_dev) cutoff = cutoff_dev[0];
     const long long i = (long long)blockIdx.x * 1024 + threadIdx.x;
     const int flag = (i < n && fabsf(r[i]) >= cutoff) ? 1 : 0;
     const unsigned b = __ballot_sync(0xffffffffu, flag);
@@ -479,9 +490,25 @@ int pdl_select_targeted(const float* points, const float* residual, int64_t n, i
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { PDL_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int64_t), st)); return 0; }
     const int nb = (int)((n + 1023) / 1024);
-    select_count_kernel<<<nb, 1024, 0, st>>>(residual, n, cutoff, block_scratch);
+    select_count_kernel<<<nb, 1024, 0, st>>>(residual, n, cutoff, nullptr, block_scratch);
     select_scan_kernel<<<1, 1024, 0, st>>>(block_scratch, nb, (long long*)out_count);
-    select_scatter_kernel<<<nb, 1024, 0, st>>>(points, residual, n, d, cutoff, block_scratch, out_points);
+    select_scatter_kernel<<<nb, 1024, 0, st>>>(points, residual, n, d, cutoff, nullptr, block_scratch, out_points);
+    PDL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int pdl_targeted_update(const float* points, const float* residual, int64_t n, int64_t n_random, int32_t d, float* out_points,
+                        int64_t* out_count, double* stats, int32_t* block_scratch, void* stream) {
+    if (!out_count || !block_scratch || !stats || n < 0 || n_random < 0 || n_random > n) return fail("bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { PDL_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int64_t), st)); return 0; }
+    if (pdl_abs_residual_moments(residual, n_random, stats, stream)) return 1;
+    float* cutoff_dev = reinterpret_cast<float*>(stats + 2);
+    cutoff_kernel<<<1, 1, 0, st>>>(stats, n_random, cutoff_dev);
+    const int nb = (int)((n + 1023) / 1024);
+    select_count_kernel<<<nb, 1024, 0, st>>>(residual, n, 0.f, cutoff_dev, block_scratch);
+    select_scan_kernel<<<1, 1024, 0, st>>>(block_scratch, nb, (long long*)out_count);
+    select_scatter_kernel<<<nb, 1024, 0, st>>>(points, residual, n, d, 0.f, cutoff_dev, block_scratch, out_points);
     PDL_CUDA(cudaGetLastError());
     return 0;
 }

@@ -197,3 +197,17 @@ if __name__ == "__main__":
              [(0.0, 1.0), (-1.0, 1.0), (-1.0, 1.0), (-1.0, 1.0)], [16, 16], "Tanh", 50, 21)
     run_training_case("training_step_heat")
     run_library_reader_case()
+
+
+def run_settings_reader_case():
+    """What the reference's Settings_Reader makes of the shipped Settings.txt (needs cwd = reference/Code)."""
+    import subprocess
+    code = ("import sys, json; sys.path.insert(0, 'Readers'); sys.path.insert(0, 'Classes'); "
+            "from Settings_Reader import Settings_Reader; S = Settings_Reader(); "
+            "S = {k: (str(v) if k == 'Device' else v) for k, v in S.items()}; "
+            "json.dump(S, open('%s', 'w'), indent=1)" % os.path.join(HERE, "settings_txt_parsed.json"))
+    subprocess.run([sys.executable, "-c", code], cwd=REF, check=True)
+
+
+if __name__ == "__main__":
+    run_settings_reader_case()

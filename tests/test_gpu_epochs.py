@@ -1,0 +1,98 @@
+"""
+Epoch-level GPU tests: the reference's own seeded training run on real Burgers data (tests/golden/burgers_run.npz,
+made by tests/golden/make_burgers_run.py with the unmodified reference on the CPU) replayed through pde_learn_b200,
+the targeted-point update, and the epoch driver.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pde_oracle as O
+from tests.helpers import GOLDEN_DIR
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+def test_burgers_run_recovers_same_xi_and_support():
+    """240 Adam epochs (random + targeted collocation points) from identical weights/data/points: same Xi trajectory
+    within tolerance and the same thresholded support as the reference run (SURVEY 8d parity gate)."""
+    import pde_learn_b200 as P
+    from pde_learn_b200 import configs
+    z = np.load(os.path.join(GOLDEN_DIR, "burgers_run.npz"))
+    W = json.loads(str(z["weights"]))
+    d, _, derivs, lhs, rhs = configs.config("burgers")                  # == Read_Library(Library.txt), tested on the CPU
+    U = P.Network([int(w) for w in z["widths"]], "Tanh", Device=_dev())
+    with torch.no_grad():
+        for j, prm in enumerate(U.parameters()):
+            prm.copy_(torch.from_numpy(z["p0_%02d" % j].copy()).to(_dev()))
+    K = len(rhs)
+    Xi = torch.zeros(K, dtype=torch.float32, device=_dev(), requires_grad=True)
+    Mask = torch.zeros(K, dtype=torch.bool)
+    opt = torch.optim.Adam(list(U.parameters()) + [Xi], lr=float(z["lr"]))
+    inputs = torch.from_numpy(z["inputs"].copy()).to(_dev()); targets = torch.from_numpy(z["targets"].copy()).to(_dev())
+    bounds = z["bounds"]; n_coll = int(z["n_coll"]); every = int(z["check_every"])
+
+    def sampler(i, e, n):                                              # the fixture's seeded CPU generator
+        g = torch.Generator().manual_seed(1000 + e)
+        u = torch.rand(n, 2, generator=g, dtype=torch.float32)
+        lo = torch.tensor(bounds[:, 0], dtype=torch.float32); hi = torch.tensor(bounds[:, 1], dtype=torch.float32)
+        return lo + (hi - lo) * u
+
+    xi_hist = []
+    hist = P.Run_Epochs([U], Xi, Mask, [inputs], [targets], [bounds], derivs, lhs, rhs, float(z["p"]), W, opt,
+                        Num_Epochs=int(z["epochs"]), Num_Train_Coll_Points=n_coll, Point_Sampler=sampler,
+                        On_Epoch=lambda e, h: xi_hist.append(Xi.detach().cpu().numpy().copy()) if (e + 1) % every == 0 else None)
+    ref_xi = z["xi_hist"]
+    dev = [float(np.max(np.abs(a - b))) for a, b in zip(xi_hist, ref_xi)]
+    print("max |xi - xi_ref| per checkpoint:", dev, " |xi_ref|max", float(np.abs(ref_xi[-1]).max()))
+    assert len(xi_hist) == ref_xi.shape[0]
+    # measured on B200: <= 7e-8 at every checkpoint (|xi| up to 0.10); gate at 1e-5 absolute
+    assert max(dev) <= 1e-5
+    sup = lambda x: [k for k in range(K) if abs(x[k]) >= 5e-4]
+    assert sup(xi_hist[-1]) == sup(ref_xi[-1])
+    assert P.Threshold_Xi(Xi, Mask) == sup(ref_xi[-1])
+    # loss histories follow the reference's (same points every epoch, so they are comparable one by one)
+    assert np.allclose(hist["Train Data"][:40, 0], z["data_hist"][:40], rtol=2e-3)
+    assert np.allclose(hist["Train Coll"][:40, 0], z["coll_hist"][:40], rtol=2e-2, atol=1e-6)
+    assert np.abs(hist["Num Targeted"][:20, 0] - z["n_targeted"][:20]).max() <= 3
+    assert abs(hist["Train Data"][-1, 0] - z["data_hist"][-1]) <= 0.05 * z["data_hist"][-1]
+
+
+def test_update_targeted_points_matches_reference_logic():
+    import pde_learn_b200 as P
+    torch.manual_seed(4)
+    n, n_rand = 50_000, 42_000
+    pts = torch.rand(n, 3, device=_dev()); r = torch.randn(n, device=_dev()); r[5] = 20.0; r[n - 2] = -30.0
+    got = P.Update_Targeted_Points(pts, r, n_rand)
+    cutoff, want = O.targeted_cutoff_select(pts.cpu(), r.cpu(), n_rand)
+    assert got.shape == want.shape and torch.equal(got.cpu(), want)
+    none = P.Update_Targeted_Points(pts[:100], torch.ones(100, device=_dev()), 100)    # std = 0: every row is >= cutoff
+    assert none.shape[0] == 100
+
+
+def test_run_epochs_two_networks_with_testing_and_device_sampler():
+    import pde_learn_b200 as P
+    from pde_learn_b200 import configs
+    torch.manual_seed(0)
+    d, bounds, derivs, lhs, rhs = configs.config("heat")
+    U_List = [P.Network([2, 16, 16, 1], "Rational", Device=_dev()) for _ in range(2)]
+    K = len(rhs)
+    Xi = torch.zeros(K, device=_dev(), requires_grad=True)
+    Mask = torch.zeros(K, dtype=torch.bool); Mask[1] = True
+    X = [P.Generate_Points(bounds, 300, _dev(), Seed=s) for s in (1, 2)]
+    Y = [torch.sin(x[:, 0]).double() * torch.cos(x[:, 1]).double() for x in X]
+    opt = torch.optim.Adam([q for U in U_List for q in U.parameters()] + [Xi], lr=2e-3)
+    W = {"Data": 1.0, "Coll": 1.0, "Lp": 1e-4, "L2": 1e-6}
+    h = P.Run_Epochs(U_List, Xi, Mask, X, Y, [bounds, bounds], derivs, lhs, rhs, 0.1, W, opt, Num_Epochs=30,
+                     Num_Train_Coll_Points=500, Num_Test_Coll_Points=200, Seed=3)
+    assert h["Train Data"].shape == (30, 2) and np.isfinite(h["Train Total"]).all() and np.isfinite(h["Test Coll"]).all()
+    assert h["Train Data"][-1].sum() < h["Train Data"][0].sum()          # it trains
+    assert float(Xi.detach()[1]) == 0.0                                            # masked coefficient never moves
+    assert (h["Num Targeted"] >= 0).all()

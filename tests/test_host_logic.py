@@ -111,3 +111,60 @@ def test_gradient_allreduce_world_size_2_gloo():
         assert torch.equal(ga, torch.full((3, 2), 3.0))
         assert torch.equal(gb, torch.arange(5.0) * 3)
         assert gc is None and counts == [201, 14]
+
+
+def test_settings_reader_matches_reference_reader(tmp_path):
+    """Our reader on the reference's shipped Settings.txt (copied text below) == the reference reader's dictionary."""
+    ref = json.load(open(os.path.join(GOLDEN_DIR, "settings_txt_parsed.json")))
+    text = """
+# Save, Load settings.
+Load U from Save [bool]:                         False
+Load Xi, Library from Save [bool]:               False
+Load Optimizer from Save [bool]:                 False
+    Load File Name [str]:
+Library File [str]:                              Library
+Hidden Layer Widths [List of int]:               20, 20, 20, 20, 20
+Hidden Activation Function [str]:                Rat
+Train on CPU or GPU [GPU, CPU]:                  gpu
+p [float]:                                       .1
+Weights [Dict of float]:                         {"Data" : 1.0, "Coll" : 1.0, "Lp" : 0.000, "L2" : 0.000005}
+Number of Training Collocation Points [int]:     3000
+Number of Testing Collocation Points [int]:      1000
+Mask Small Xi Components [bool]:                 True     # trailing comment
+Optimizer [Adam, LBFGS]:                         Adam
+Learning Rate [float]:                           .001
+Number of Epochs [int]:                          1000
+DataSet Names [List of str]:                     [Burgers_Sine_N75_P2000]
+"""
+    f = tmp_path / "Settings.txt"
+    f.write_text(text)
+    S = P.Settings_Reader(str(f))
+    for k, v in ref.items():
+        if k in ("Device", "Library Path"):
+            continue
+        assert S[k] == v, k
+    assert S["Device"].type == "cuda" and S["Library Path"].endswith("Library.txt")
+    f.write_text(text.replace("gpu", "cpu"))
+    with pytest.raises(P.Read_Error):
+        P.Settings_Reader(str(f))                      # no CPU path: refuse instead of silently switching
+
+
+def test_save_load_state_round_trip(tmp_path):
+    torch.manual_seed(1)
+    d, _, derivs, lhs, rhs = configs.config("heat")
+    U = P.Network([2, 12, 12, 1], "Rational")
+    Xi = torch.randn(len(rhs), requires_grad=True)
+    opt = torch.optim.Adam(list(U.parameters()) + [Xi], lr=1e-3)
+    path = str(tmp_path / "save")
+    P.Save_State(path, [U], Xi, opt, derivs, lhs, rhs, ["Heat"])
+    blob = torch.load(path, weights_only=False)
+    assert sorted(blob.keys()) == sorted(["U States", "Xi", "Optimizer", "Derivative Encodings", "LHS Term State",
+                                          "RHS Term States", "DataSet Names"])          # Code/main.py:517-523
+    st = P.Load_State(path, torch.device("cpu"))
+    V = st["U List"][0]
+    x = torch.rand(4, 2)
+    assert torch.equal(U(x), V(x)) and torch.equal(st["Xi"], Xi)
+    assert [D.Encoding.tolist() for D in st["Derivatives"]] == [D.Encoding.tolist() for D in derivs]
+    assert str(st["LHS Term"]) == str(lhs) and [str(t) for t in st["RHS Terms"]] == [str(t) for t in rhs]
+    assert P.Threshold_Xi(torch.tensor([0.1, 1e-4, -0.2]), torch.tensor([False, False, True])) == [0]
+    assert P.Build_Mask(torch.tensor([0.1, 1e-4, -0.2])).tolist() == [False, True, False]
