@@ -137,6 +137,11 @@ int pdl_targeted_update(const float* points, const float* residual, int64_t n, i
 int pdl_adam_step(float* theta, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
                   double beta1, double beta2, double eps, int64_t step, void* stream);
 
+/* out[i] = wa*a[i] + wb*b[i] + wc*c[i] (b, c may be NULL): the weighted sum wC*dColl + wD*dData + wL2*dL2 of one
+ * closure (Code/Test_Train.py:167-170) in a single pass over the flat gradient vectors. */
+int pdl_axpby3(float* out, int64_t n, const float* a, double wa, const float* b, double wb, const float* c, double wc,
+               void* stream);
+
 /* Register-resident FFMA-chain microbenchmark: measured FP32 peak of the current device in TFLOP/s
  * (the roofline denominator).  Synchronises the stream. */
 int pdl_measure_fp32_peak(double* tflops, void* stream);

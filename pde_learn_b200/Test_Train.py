@@ -18,6 +18,7 @@ from typing import Dict, List
 import torch
 
 from .Loss import Coll_Loss, Data_Loss, L2_Squared_Loss, Lp_Loss
+from .engine import closure_total
 
 
 def _global_counts(local_counts: List[int], group) -> List[int]:
@@ -66,38 +67,29 @@ def Training(U_List: List, Xi: torch.Tensor, Mask: torch.Tensor, Coll_Points_Lis
     def Closure() -> torch.Tensor:
         if torch.is_grad_enabled():
             Optimizer.zero_grad()
-        lp = Lp_Loss(Xi=Xi, Mask=Mask, p=p)
-        total = None
-        colls, datas, l2s, totals, residuals = [], [], [], [], []
-        for i in range(S):
-            c, r = Coll_Loss(U=U_List[i], Xi=Xi, Mask=Mask, Coll_Points=Coll_Points_List[i], Derivatives=Derivatives,
-                             LHS_Term=LHS_Term, RHS_Terms=RHS_Terms, Inv_N=1.0 / max(n_coll[i], 1))
-            d = Data_Loss(U=U_List[i], Inputs=Inputs_List[i], Targets=Targets_List[i], Inv_N=1.0 / max(n_data[i], 1))
-            l2 = L2_Squared_Loss(U=U_List[i])
-            t = (Weights["Data"] * d + Weights["Coll"] * c + (Weights["Lp"] / world) * lp + (Weights["L2"] / world) * l2)
-            colls.append(c.detach()); datas.append(d.detach()); l2s.append(l2.detach().reshape(())); totals.append(t.detach().reshape(()))
-            residuals.append(r)
-            total = t if total is None else total + t
+        # the whole closure is one autograd node (engine._ClosureFn): Lp + per network Coll/Data/L2 and the
+        # weighted combination of their gradients are launched back to back, no per-loss host syncs
+        total, scalars, residuals = closure_total(U_List, Xi, Mask, Coll_Points_List, Inputs_List, Targets_List, Derivatives,
+                                                  LHS_Term, RHS_Terms, p, Weights,
+                                                  inv_n_coll=[1.0 / max(n, 1) for n in n_coll],
+                                                  inv_n_data=[1.0 / max(n, 1) for n in n_data], world=world)
         if total.requires_grad:
             total.backward()
             if Process_Group is not None:
                 params = [q for U in U_List for q in U.parameters()] + [Xi]
                 allreduce_gradients(params, Process_Group)
-        last.update(colls=colls, datas=datas, l2s=l2s, totals=totals, residuals=residuals, lp=lp.detach())
-        return total.reshape(1).to(torch.float32)
+        last.update(scalars=scalars, residuals=residuals)
+        return total.reshape(1)
 
     Optimizer.step(Closure)
 
-    # one device->host copy for all reported scalars
-    pack = torch.stack([v.to(torch.float64) for v in last["colls"] + last["datas"] + last["l2s"] + last["totals"]] +
-                       [last["lp"].to(torch.float64)])
+    # one device->host copy for all reported scalars: [coll_*, data_*, l2_*, total_*, lp]
+    pack = last["scalars"].clone()
     if Process_Group is not None:
         import torch.distributed as dist
-        red = pack.clone()
-        red[2 * S:3 * S] /= world                     # L2 is replicated, everything else is a partial sum
-        red[4 * S] /= world
-        dist.all_reduce(red, group=Process_Group)
-        pack = red
+        pack[2 * S:3 * S] /= world                    # L2 and Lp are replicated, everything else is a partial sum
+        pack[4 * S] /= world
+        dist.all_reduce(pack, group=Process_Group)
     host = pack.cpu().tolist()
     res = [r.detach() for r in last["residuals"]]
     if Residuals_Device == "cpu":

@@ -17,6 +17,7 @@ from .Loss import Coll_Loss, Data_Loss, Lp_Loss, L2_Squared_Loss            # no
 from .Evaluate_Derivatives import Evaluate_Derivatives, Derivative_From_Derivative   # noqa: F401
 from .Points import Generate_Points                                         # noqa: F401
 from .Test_Train import Training, Testing, allreduce_gradients              # noqa: F401
+from .engine import closure_total as Closure_Loss                          # noqa: F401
 from .Library_Reader import Read_Library, Parse_Term                        # noqa: F401
 from .Settings_Reader import Settings_Reader, Read_Error                     # noqa: F401
 from .Driver import (Update_Targeted_Points, Run_Epochs, Build_Mask, Threshold_Xi, Save_State, Load_State)   # noqa: F401

@@ -62,6 +62,8 @@ PROTOTYPES = {
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdl_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
                                 C.c_double, C.c_double, C.c_double, C.c_int64, C.c_void_p]),
+    "pdl_axpby3": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_double,
+                             C.c_void_p]),
     "pdl_measure_fp32_peak": (C.c_int, [C.POINTER(C.c_double), C.c_void_p]),
 }
 

@@ -421,6 +421,18 @@ __global__ void adam_kernel(float* __restrict__ th, const float* __restrict__ g,
     }
 }
 
+// ---- out = wa*a + wb*b + wc*c (b, c optional): combines the per-term gradients of one closure ----
+__global__ void axpby3_kernel(float* __restrict__ out, long long n, const float* __restrict__ a, float wa,
+                              const float* __restrict__ b, float wb, const float* __restrict__ c, float wc) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float v = wa * a[i];
+        if (b) v += wb * b[i];
+        if (c) v += wc * c[i];
+        out[i] = v;
+    }
+}
+
 // ---- FP32 peak: 8 independent FFMA chains per thread ----
 __global__ void fp32_peak_kernel(float* out, int iters, float a, float b) {
     float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
@@ -521,6 +533,15 @@ int pdl_adam_step(float* theta, const float* grad, float* m, float* v, int64_t n
     if (blocks > 148 * 8) blocks = 148 * 8;
     adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(theta, grad, m, v, n, (float)(lr / c1), (float)b1, (float)b2,
                                                                (float)(1.0 / sqrt(c2)), (float)eps);
+    PDL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int pdl_axpby3(float* out, int64_t n, const float* a, double wa, const float* b, double wb, const float* c, double wc, void* stream) {
+    if (!out || !a || n <= 0) return fail("bad axpby3 arguments");
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    axpby3_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(out, n, a, (float)wa, b, (float)wb, c, (float)wc);
     PDL_CUDA(cudaGetLastError());
     return 0;
 }

@@ -270,3 +270,117 @@ class _L2LossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         return tuple(_split_flat(ctx.grad * g, ctx.shapes))
+
+
+# ----------------------------------------------------------------------------------------------
+# fused closure: the whole  sum_i [wD Data_i + wC Coll_i + wLp Lp + wL2 L2_i]  as ONE autograd node
+# ----------------------------------------------------------------------------------------------
+
+class ClosureSpec:
+    """Everything that is not a differentiable tensor (kept out of autograd's argument handling)."""
+
+    def __init__(self, U_List, Mask, Coll_Points_List, Inputs_List, Targets_List, Derivatives, LHS_Term, RHS_Terms, p, Weights,
+                 inv_n_coll, inv_n_data, world):
+        self.S = len(U_List)
+        self.coll_plans = [collocation_plan(U, Derivatives, LHS_Term, RHS_Terms) for U in U_List]
+        self.data_plans = [data_plan(U) for U in U_List]
+        self.n_tensors = [len(network_param_tensors(U)) for U in U_List]
+        self.points = [_check_cuda_f32(P, "Coll_Points").detach() for P in Coll_Points_List]
+        self.inputs = [_check_cuda_f32(X, "Inputs").detach() for X in Inputs_List]
+        self.targets = []
+        for X, Y in zip(self.inputs, Targets_List):
+            if not Y.is_cuda:
+                raise RuntimeError("Targets must be CUDA tensors: this engine has no CPU path")
+            Y = Y.reshape(-1).to(torch.float64).contiguous()
+            assert Y.numel() == X.shape[0]
+            self.targets.append(Y)
+        self.K = self.coll_plans[0].K
+        self.mask_dev = device_mask(Mask, self.K, self.points[0].device)
+        self.p, self.W, self.world = float(p), dict(Weights), int(world)
+        self.inv_n_coll, self.inv_n_data = list(inv_n_coll), list(inv_n_data)
+
+
+class _ClosureFn(torch.autograd.Function):
+    """
+    forward: launches Lp, and per network the fused collocation kernel, the fused data kernel and L2, then combines
+    the flat gradients with the loss weights (one axpby3 pass per network).  Returns (total, scalars, *residuals):
+    scalars = [coll_0..coll_{S-1}, data_*, l2_*, total_*, lp] (float64, device).  backward only rescales.
+    """
+
+    @staticmethod
+    def forward(ctx, spec: ClosureSpec, want_grad: bool, xi, *params):
+        S, K, W, world = spec.S, spec.K, spec.W, spec.world
+        dev = xi.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        lib = L.lib()
+        lp = torch.empty(1, dtype=torch.float32, device=dev)
+        g_lp = torch.empty(K, dtype=torch.float32, device=dev)
+        stats_c = torch.empty((S, 4), dtype=torch.float64, device=dev)
+        stats_d = torch.empty((S, 4), dtype=torch.float64, device=dev)
+        l2 = torch.empty(S, dtype=torch.float32, device=dev)
+        gx = torch.empty((S, max(K, 1)), dtype=torch.float32, device=dev) if want_grad else None
+        residuals, grads = [], []
+        with torch.cuda.device(dev):
+            L.check(lib.pdl_lp_loss(xi.data_ptr(), spec.mask_dev.data_ptr(), K, spec.p, lp.data_ptr(), g_lp.data_ptr(), stream))
+            off = 0
+            for i in range(S):
+                prm = params[off:off + spec.n_tensors[i]]
+                off += spec.n_tensors[i]
+                cp, dp = spec.coll_plans[i], spec.data_plans[i]
+                P = cp.n_param_scalars
+                res = torch.empty(spec.points[i].shape[0], dtype=torch.float32, device=dev)
+                gc = torch.empty(P, dtype=torch.float32, device=dev) if want_grad else None
+                gd = torch.empty(P, dtype=torch.float32, device=dev) if want_grad else None
+                g2 = torch.empty(P, dtype=torch.float32, device=dev) if want_grad else None
+                cp.launch(spec.points[i], prm, xi, spec.mask_dev, None, spec.inv_n_coll[i], want_grad, res, None, gc,
+                          gx[i] if want_grad else None, stats_c[i])
+                dp.launch(spec.inputs[i], prm, None, None, spec.targets[i], spec.inv_n_data[i], want_grad, None, None, gd, None,
+                          stats_d[i])
+                n = len(prm)
+                ptrs = (C.c_void_p * n)(*[q.data_ptr() for q in prm])
+                sizes = (C.c_int32 * n)(*[int(q.numel()) for q in prm])
+                L.check(lib.pdl_l2_squared_loss(ptrs, sizes, n, l2[i:i + 1].data_ptr(), g2.data_ptr() if want_grad else None, stream))
+                if want_grad:
+                    L.check(lib.pdl_axpby3(gc.data_ptr(), P, gc.data_ptr(), W["Coll"], gd.data_ptr(), W["Data"], g2.data_ptr(),
+                                           W["L2"] / world, stream))
+                    grads.append(gc)
+                residuals.append(res)
+        coll, data = stats_c[:, 0], stats_d[:, 0]
+        l2d, lpd = l2.to(torch.float64), lp.to(torch.float64)
+        totals = W["Data"] * data + W["Coll"] * coll + (W["Lp"] / world) * lpd + (W["L2"] / world) * l2d
+        scalars = torch.cat([coll, data, l2d, totals, lpd])
+        ctx.grads = grads
+        ctx.gxi = (W["Coll"] * gx.sum(0)[:K] + (S * W["Lp"] / world) * g_lp) if want_grad else None
+        ctx.shapes = [q.shape for q in params]
+        ctx.n_tensors = spec.n_tensors
+        for r in residuals:
+            ctx.mark_non_differentiable(r)
+        ctx.mark_non_differentiable(scalars)
+        return (totals.sum().to(torch.float32), scalars, *residuals)
+
+    @staticmethod
+    def backward(ctx, g_total, _g_scalars, *_g_res):
+        if ctx.gxi is None:
+            raise RuntimeError("the closure was evaluated without gradients")
+        out, off = [], 0
+        for i, g in enumerate(ctx.grads):
+            out += _split_flat(g * g_total, ctx.shapes[off:off + ctx.n_tensors[i]])
+            off += ctx.n_tensors[i]
+        return (None, None, ctx.gxi * g_total, *out)
+
+
+def closure_total(U_List, Xi, Mask, Coll_Points_List, Inputs_List, Targets_List, Derivatives, LHS_Term, RHS_Terms, p, Weights,
+                  inv_n_coll=None, inv_n_data=None, world=1):
+    """(total, scalars, residuals): see _ClosureFn.  `total` is differentiable w.r.t. Xi and every network parameter."""
+    assert torch.numel(Xi) == len(RHS_Terms)
+    assert p > 0 and p < 2
+    S = len(U_List)
+    inv_c = inv_n_coll or [1.0 / max(int(P.shape[0]), 1) for P in Coll_Points_List]
+    inv_d = inv_n_data or [1.0 / max(int(X.shape[0]), 1) for X in Inputs_List]
+    spec = ClosureSpec(U_List, Mask, Coll_Points_List, Inputs_List, Targets_List, Derivatives, LHS_Term, RHS_Terms, p, Weights,
+                       inv_c, inv_d, world)
+    params = [_check_cuda_f32(q, "network parameter") for U in U_List for q in network_param_tensors(U)]
+    xi = _check_cuda_f32(Xi, "Xi")
+    want = torch.is_grad_enabled() and (xi.requires_grad or any(q.requires_grad for q in params))
+    out = _ClosureFn.apply(spec, want, xi, *params)
+    return out[0], out[1], list(out[2:2 + S])

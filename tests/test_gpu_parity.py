@@ -295,3 +295,41 @@ def test_no_cpu_fallback():
         P.Coll_Loss(U, g.xi, torch.tensor(g.mask), g.points, derivs, lhs, rhs)
     with pytest.raises(TypeError):                      # a bare callable (reference tests use polynomials) is refused
         P.Coll_Loss(lambda X: X.sum(1), g.xi.to(_dev()), torch.tensor(g.mask), g.points.to(_dev()), derivs, lhs, rhs)
+
+
+def test_fused_closure_equals_separate_losses():
+    """engine._ClosureFn (one autograd node) == wD*Data + wC*Coll + wLp*Lp + wL2*L2 assembled from the separate ops."""
+    import pde_learn_b200 as P
+    from pde_learn_b200 import configs
+    torch.manual_seed(5)
+    d, bounds, derivs, lhs, rhs = configs.config("kdv")
+    U_List = [P.Network([d, 24, 24, 24, 1], act, Device=_dev()) for act in ("Rational", "Rational")]
+    K = len(rhs)
+    Xi = (0.1 * torch.randn(K)).to(_dev()).requires_grad_(True)
+    Mask = torch.zeros(K, dtype=torch.bool); Mask[2] = True
+    coll = [P.Generate_Points(bounds, n, _dev(), Seed=7 + n) for n in (777, 1030)]
+    X = [P.Generate_Points(bounds, 99, _dev(), Seed=3), P.Generate_Points(bounds, 64, _dev(), Seed=4)]
+    Y = [torch.randn(99, dtype=torch.float64, device=_dev()), torch.randn(64, dtype=torch.float64, device=_dev())]
+    W = {"Data": 0.7, "Coll": 1.3, "Lp": 3e-3, "L2": 2e-5}
+    params = [q for U in U_List for q in U.parameters()] + [Xi]
+
+    total, scalars, res = P.Closure_Loss(U_List, Xi, Mask, coll, X, Y, derivs, lhs, rhs, 0.3, W)
+    total.backward()
+    g_fused = [q.grad.clone() for q in params]
+    for q in params:
+        q.grad = None
+    lp = P.Lp_Loss(Xi, Mask, 0.3)
+    ref_total = 0
+    for i in range(2):
+        c, r = P.Coll_Loss(U_List[i], Xi, Mask, coll[i], derivs, lhs, rhs)
+        dl = P.Data_Loss(U_List[i], X[i], Y[i])
+        l2 = P.L2_Squared_Loss(U_List[i])
+        ref_total = ref_total + W["Data"] * dl + W["Coll"] * c + W["Lp"] * lp + W["L2"] * l2
+        assert torch.equal(r, res[i])
+        assert abs(float(scalars[i]) - float(c.detach())) <= 1e-6 * abs(float(c.detach()))
+        assert abs(float(scalars[2 + i]) - float(dl.detach())) <= 1e-12
+    ref_total.sum().backward()
+    assert abs(float(total.detach()) - float(ref_total.detach().sum())) <= 2e-6 * abs(float(ref_total.detach().sum()))
+    for a, q in zip(g_fused, params):
+        assert float((a - q.grad).abs().max()) <= 2e-6 * float(q.grad.abs().max() + 1e-30)
+    assert float(g_fused[-1][2]) == 0.0
