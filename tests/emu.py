@@ -16,6 +16,7 @@ from pde_learn_b200 import _lib as L
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "pde_learn_b200", "csrc")
 EMU_DIR = os.path.join(ROOT, "tests", "_emu_build")
+EXTRA_FLAGS = []          # e.g. sanitizers (tests/test_emulation_asan.py)
 
 
 class KernelParams(C.Structure):
@@ -35,7 +36,7 @@ def build_emu(desc):
         cpp = os.path.join(EMU_DIR, "emu_%s.cpp" % tag)
         with open(cpp, "w") as f:
             f.write(src)
-        cmd = ["g++", "-O1", "-std=c++17", "-DPDL_EMULATE", "-shared", "-fPIC", "-I", CSRC, "-o", so, cpp]
+        cmd = ["g++", "-O1", "-std=c++17", "-DPDL_EMULATE", "-shared", "-fPIC", "-I", CSRC] + EXTRA_FLAGS + ["-o", so, cpp]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("emulation build failed:\n" + r.stderr[-4000:])
