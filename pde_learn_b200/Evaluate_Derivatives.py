@@ -45,3 +45,20 @@ def Derivative_From_Derivative(Da, Db, Db_U, Coords):
     raise NotImplementedError(
         "Derivative_From_Derivative differentiates an autograd graph (Code/Evaluate_Derivatives.py:104-205); the "
         "B200 engine propagates jets through the network instead. Call Evaluate_Derivatives(U, Derivatives, Coords).")
+
+
+def Evaluate_Residual(U, Xi: torch.Tensor, Mask: torch.Tensor, Coords: torch.Tensor, Derivatives: List, LHS_Term, RHS_Terms: List
+                      ) -> torch.Tensor:
+    """
+    PDE residual T_0(U) - sum_k xi_k T_k(U) at every row of Coords, forward-only kernel, any number of rows in one call.
+    This is what Plot/Plot_One_Spatial_Dimension.py:149-178 gets from Coll_Loss in batches of 1000 points (pass the real
+    mask here: the reference's plot passes an all-True mask and therefore shows b(U) only).
+    """
+    from .Loss import Coll_Loss
+    with torch.no_grad():
+        return Coll_Loss(U, Xi, Mask, Coords, Derivatives, LHS_Term, RHS_Terms)[1]
+
+
+def Evaluate_Network(U, Coords: torch.Tensor) -> torch.Tensor:
+    """U(Coords) as a [B] float32 tensor through the forward-only kernel (same numbers the losses see)."""
+    return Evaluate_Derivatives(U, [Derivative(Encoding=np.array([0, 0]))], Coords)[0]

@@ -14,7 +14,8 @@ from .Derivative import Derivative, Get_Order                               # no
 from .Term import Term, Build_Term_From_State                               # noqa: F401
 from .Network import Network, Rational                                      # noqa: F401
 from .Loss import Coll_Loss, Data_Loss, Lp_Loss, L2_Squared_Loss            # noqa: F401
-from .Evaluate_Derivatives import Evaluate_Derivatives, Derivative_From_Derivative   # noqa: F401
+from .Evaluate_Derivatives import (Evaluate_Derivatives, Derivative_From_Derivative, Evaluate_Residual,
+                                   Evaluate_Network)                       # noqa: F401
 from .Points import Generate_Points                                         # noqa: F401
 from .Test_Train import Training, Testing, allreduce_gradients              # noqa: F401
 from .engine import closure_total as Closure_Loss                          # noqa: F401

@@ -1,0 +1,239 @@
+// tcgen05 / TMEM building block for the next-round tensor-core contraction (groundwork, not the product path).
+//
+//   test 1: D[128 x 48] = A[128 x 40] * B[48 x 40]^T, kind::tf32, both operands K-major, no swizzle, layout [k/4][row][4]
+//   test 2: the same with the 3xTF32 split (Ahi*Bhi + Ahi*Blo + Alo*Bhi), error against float64
+//   test 3: W[64 x 48] = Z^T * H with Z [128 x 40], H [128 x 40] read MN-major from the SAME [chunk][row][4] buffers
+//           (the weight-gradient shape: K = points) -- also prints which TMEM lanes an M=64 accumulator uses
+//   test 4: sustained rate of the 15-MMA (5 k-steps x 3 splits) layer contraction on all SMs
+//
+// Shared-memory descriptor and instruction descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp (CUTLASS).
+// Every wait is bounded so a wrong descriptor cannot hang the GPU.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;          // version = 1 (Blackwell)
+    return d;                        // layout_type = 0 (no swizzle), base_offset = 0
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc),
+                 "r"(accumulate));
+}
+__device__ __forceinline__ void commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (long long it = 0; it < 20000000LL; ++it) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ void ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+constexpr int KP = 40, NP = 48, MP = 128;
+constexpr int KC = KP / 4;                       // 16-byte chunks along K
+
+struct Smem {
+    float A[2][KC][MP][4];                       // [hi/lo][chunk][row][4]
+    float B[2][KC][NP][4];
+    uint64_t bar;
+    uint32_t tmem_base;
+    int failed;
+};
+
+// mode 0: plain tf32;  1: 3xTF32;  2: MN-major weight-gradient shape (A = B-operand... see above);  3: timing loop
+__global__ void __launch_bounds__(128, 1) tc_kernel(const float* __restrict__ Ag, const float* __restrict__ Bg, float* __restrict__ Dg,
+                                                    int mode, int iters, long long* cycles, int* status) {
+    extern __shared__ __align__(1024) unsigned char raw[];
+    Smem& S = *reinterpret_cast<Smem*>(raw);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        S.failed = 0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&S.bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;\n" ::"r"(smem_u32(&S.tmem_base)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    // stage A (128 x 40) and B (48 x 40) as hi/lo tf32 pieces, layout [chunk][row][4]
+    for (int e = tid; e < MP * KP; e += 128) {
+        const int m = e / KP, k = e % KP;
+        const float a = Ag[e];
+        const float hi = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+        S.A[0][k / 4][m][k % 4] = (mode == 0 || mode == 2) ? a : hi;
+        S.A[1][k / 4][m][k % 4] = a - hi;
+    }
+    for (int e = tid; e < NP * KP; e += 128) {
+        const int n = e / KP, k = e % KP;
+        const float b = Bg[e];
+        const float hi = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+        S.B[0][k / 4][n][k % 4] = (mode == 0 || mode == 2) ? b : hi;
+        S.B[1][k / 4][n][k % 4] = b - hi;
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem = S.tmem_base;
+    uint32_t parity = 0;
+    long long t0 = clock64();
+    const int reps = (mode == 3) ? iters : 1;
+    for (int rep = 0; rep < reps; ++rep) {
+        if (tid == 0) {
+            if (mode == 2) {
+                // W[64 x 48] = sum_p Z[p][n] * H[p][k]: A = Z read MN-major (M = n, K = p), B = H read MN-major (N = k, K = p)
+                // element (m, kk) of an MN-major operand lives at unit (m/4)*SBO + (kk%8) + (kk/8)*LBO, with our buffers
+                // [chunk = m/4][row = p][4]:  SBO = 128 rows * 16 B,  LBO = 8 rows * 16 B.  Here "B" has only 48 rows per chunk.
+                const uint32_t idesc = make_idesc(64, 48, 1, 1);
+                for (int ks = 0; ks < MP / 8; ++ks) {                // K = 128 points, 8 per MMA
+                    const uint64_t ad = make_desc(smem_u32(&S.A[0][0][ks * 8][0]), 8 * 16, MP * 16);
+                    const uint64_t bd = make_desc(smem_u32(&S.A[1][0][ks * 8][0]), 8 * 16, MP * 16);   // second operand parked in A[1]
+                    mma_tf32(tmem, ad, bd, idesc, ks > 0);
+                }
+            } else {
+                const uint32_t idesc = make_idesc(128, NP, 0, 0);
+                const int nsplit = (mode == 0) ? 1 : 3;
+                bool first = true;
+                for (int ks = 0; ks < KP / 8; ++ks) {
+                    for (int sp = 0; sp < nsplit; ++sp) {
+                        const int ia = (sp == 2) ? 1 : 0, ib = (sp == 1) ? 1 : 0;   // hi*hi, hi*lo, lo*hi
+                        const uint64_t ad = make_desc(smem_u32(&S.A[ia][2 * ks][0][0]), MP * 16, 8 * 16);
+                        const uint64_t bd = make_desc(smem_u32(&S.B[ib][2 * ks][0][0]), NP * 16, 8 * 16);
+                        mma_tf32(tmem, ad, bd, idesc, first ? 0u : 1u);
+                        first = false;
+                    }
+                }
+            }
+            commit(&S.bar);
+        }
+        if (!wait_bar(&S.bar, parity)) { S.failed = 1; break; }
+        parity ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    }
+    long long t1 = clock64();
+    __syncthreads();
+    if (tid == 0) { cycles[blockIdx.x] = t1 - t0; status[blockIdx.x] = S.failed; }
+    if (!S.failed && blockIdx.x == 0) {
+        // every thread reads its TMEM lane (= row): 48 columns
+        for (int c = 0; c < NP; c += 8) {
+            float v[8];
+            ld8(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+            for (int i = 0; i < 8; ++i) Dg[tid * NP + c + i] = v[i];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;\n" ::"r"(tmem));
+}
+
+static float tf32_trunc(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; float y; memcpy(&y, &u, 4); return y; }
+
+int main() {
+    cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0);
+    const int sms = prop.multiProcessorCount;
+    std::vector<float> A(MP * KP), B(NP * KP), Z(MP * KP), H(MP * KP), D(MP * NP);
+    srand(1);
+    for (auto& v : A) v = (float)rand() / RAND_MAX * 2 - 1;
+    for (auto& v : B) v = (float)rand() / RAND_MAX * 2 - 1;
+    float *dA, *dB, *dD; long long* dC; int* dS;
+    cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dB, B.size() * 4); cudaMalloc(&dD, D.size() * 4);
+    cudaMalloc(&dC, sms * 8); cudaMalloc(&dS, sms * 4);
+    cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
+    const int smem = sizeof(Smem) + 1024;
+    cudaFuncSetAttribute(tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    printf("smem per CTA %d bytes\n", smem);
+    int st = 0; long long cyc = 0;
+    for (int mode = 0; mode < 2; ++mode) {
+        cudaMemset(dD, 0, D.size() * 4);
+        tc_kernel<<<1, 128, smem>>>(dA, dB, dD, mode, 1, dC, dS);
+        cudaError_t e = cudaDeviceSynchronize();
+        cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost);
+        printf("mode %d: launch %s, wait %s\n", mode, cudaGetErrorString(e), st ? "TIMED OUT" : "ok");
+        if (e != cudaSuccess || st) return 1;
+        cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+        double emax = 0, rmax = 0, emax_t = 0;
+        for (int m = 0; m < MP; ++m)
+            for (int n = 0; n < NP; ++n) {
+                double ref = 0, ref_t = 0;
+                for (int k = 0; k < KP; ++k) {
+                    ref += (double)A[m * KP + k] * B[n * KP + k];
+                    ref_t += (double)tf32_trunc(A[m * KP + k]) * tf32_trunc(B[n * KP + k]);
+                }
+                emax = fmax(emax, fabs(D[m * NP + n] - ref)); rmax = fmax(rmax, fabs(ref));
+                emax_t = fmax(emax_t, fabs(D[m * NP + n] - ref_t));
+            }
+        printf("mode %d (%s): max|D - fp64| = %.3e (rel to max %.3e), max|D - tf32-truncated ref| = %.3e\n", mode,
+               mode ? "3xTF32" : "tf32", emax, emax / rmax, emax_t);
+    }
+    {   // MN-major weight-gradient shape: Z = A buffer (128 x 40), H stored in the A[1] slot -> upload H as the 'lo' part trick:
+        // the kernel builds A[1] = a - hi, so feed mode 2 with raw copies instead: A[0] = Z, A[1] = Z - trunc(Z) is not H.
+        // Simplest: use Z for both operands (W = Z^T Z restricted to 64 x 48), which still checks layout and lane mapping.
+        cudaMemset(dD, 0, D.size() * 4);
+        tc_kernel<<<1, 128, smem>>>(dA, dB, dD, 2, 1, dC, dS);
+        cudaError_t e = cudaDeviceSynchronize();
+        cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost);
+        printf("mode 2: launch %s, wait %s\n", cudaGetErrorString(e), st ? "TIMED OUT" : "ok");
+        if (e == cudaSuccess && !st) {
+            cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+            // expected W[n][k] = sum_p trunc(Z[p][n]) * trunc(L[p][k]) with L = Z - trunc(Z) (what the kernel parked in A[1])
+            std::vector<double> Wref(40 * 40);
+            for (int n = 0; n < 40; ++n)
+                for (int k = 0; k < 40; ++k) {
+                    double ref = 0;
+                    for (int p = 0; p < MP; ++p) { float z = A[p * KP + k]; ref += (double)tf32_trunc(A[p * KP + n]) * tf32_trunc(z - tf32_trunc(z)); }
+                    Wref[n * 40 + k] = ref;
+                }
+            printf("  expected W[0][0..3] = %.4e %.4e %.4e %.4e ; W[1][0..3] = %.4e %.4e %.4e %.4e\n", Wref[0], Wref[1], Wref[2], Wref[3],
+                   Wref[40], Wref[41], Wref[42], Wref[43]);
+            for (int lane = 0; lane < 128; lane += (lane < 20 ? 1 : 8))
+                printf("  lane %3d: %.4e %.4e %.4e %.4e | col 8: %.4e\n", lane, D[lane * NP], D[lane * NP + 1], D[lane * NP + 2], D[lane * NP + 3], D[lane * NP + 8]);
+            // match every (lane, col) against every (n, k)
+            int hits = 0;
+            for (int lane = 0; lane < 128 && hits < 24; ++lane)
+                for (int c = 0; c < 4; ++c)
+                    for (int n = 0; n < 40; ++n)
+                        for (int k = 0; k < 40; ++k)
+                            if (fabs(D[lane * NP + c] - Wref[n * 40 + k]) < 1e-9 + 1e-5 * fabs(Wref[n * 40 + k]) && fabs(Wref[n * 40 + k]) > 1e-6) {
+                                if (hits < 24) printf("  D[lane %d][col %d] == W[n=%d][k=%d]\n", lane, c, n, k);
+                                ++hits;
+                            }
+        }
+    }
+    for (int iters : {2000}) {
+        tc_kernel<<<sms, 128, smem>>>(dA, dB, dD, 3, iters, dC, dS);
+        cudaError_t e = cudaDeviceSynchronize();
+        cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost); cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost);
+        const double mmas = 15.0 * iters;
+        printf("mode 3: %s %s: %.1f cycles per 15-MMA layer contraction (128x48x40, 3xTF32) incl. commit+wait = %.1f cycles/MMA; "
+               "useful FMA/clk/SM = %.0f\n", cudaGetErrorString(e), st ? "TIMED OUT" : "ok", (double)cyc / iters, (double)cyc / mmas,
+               128.0 * 48 * 40 * iters / (double)cyc);
+    }
+    return 0;
+}

@@ -333,3 +333,18 @@ def test_fused_closure_equals_separate_losses():
     for a, q in zip(g_fused, params):
         assert float((a - q.grad).abs().max()) <= 2e-6 * float(q.grad.abs().max() + 1e-30)
     assert float(g_fused[-1][2]) == 0.0
+
+
+def test_forward_only_helpers():
+    """Evaluate_Network / Evaluate_Residual (the plotting callers of SURVEY 8f row 4) agree with torch and with Coll_Loss."""
+    import pde_learn_b200 as P
+    g = GoldenCase("burgers_rational20")
+    U = _network_from_golden(g, P)
+    derivs, lhs, rhs = _terms(P, g.lhs, g.rhs)
+    pts = g.points.to(_dev())
+    u = P.Evaluate_Network(U, pts)
+    with torch.no_grad():
+        ref = U(pts).reshape(-1)
+    assert float((u - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+    r = P.Evaluate_Residual(U, g.xi.to(_dev()), torch.tensor(g.mask), pts, derivs, lhs, rhs)
+    assert rel_max(r.cpu().numpy(), g.z["residual"]) <= TOL and not r.requires_grad
