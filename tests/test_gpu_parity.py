@@ -348,3 +348,63 @@ def test_forward_only_helpers():
     assert float((u - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
     r = P.Evaluate_Residual(U, g.xi.to(_dev()), torch.tensor(g.mask), pts, derivs, lhs, rhs)
     assert rel_max(r.cpu().numpy(), g.z["residual"]) <= TOL and not r.requires_grad
+
+
+def _shape_cases():
+    from tests.test_emulation_shapes import CASES
+    return CASES
+
+
+@pytest.mark.parametrize("case", _shape_cases(), ids=[c[0] for c in _shape_cases()])
+def test_unusual_architectures_vs_oracle(case):
+    """The architectures/libraries of tests/test_emulation_shapes.py on the device, through the public API."""
+    import pde_learn_b200 as P
+    name, d, hidden, act, lhs, rhs, n, masked = case
+    n = 8 * n + 3
+    torch.manual_seed(11)
+    U = P.Network([d] + hidden + [1], "Rational" if act == "rational" else "Tanh", Device=_dev())
+    with torch.no_grad():
+        for l in U.Layers:
+            l.bias.normal_(0, 0.1)
+    derivs, LHS, RHS = _terms(P, lhs, rhs)
+    K = len(rhs)
+    xi = (0.3 * torch.randn(K)).to(_dev()).requires_grad_(True)
+    mask = torch.tensor([k in masked for k in range(K)], dtype=torch.bool)
+    pts = (torch.rand(n, d) * 2 - 1).to(_dev())
+    loss, resid = P.Coll_Loss(U, xi, mask, pts, derivs, LHS, RHS)
+    loss.backward()
+    ra = [a.a.detach().cpu() for a in list(U.Activation_Functions)[:-1]] if act == "rational" else []
+    rb = [a.b.detach().cpu() for a in list(U.Activation_Functions)[:-1]] if act == "rational" else []
+    net = O.NetParams([l.weight.detach().cpu() for l in U.Layers], [l.bias.detach().cpu() for l in U.Layers], act, ra, rb).to(torch.float64, True)
+    xi64 = xi.detach().cpu().double().requires_grad_(True)
+    ol, orr, _ = O.coll_loss(lambda X: O.mlp_forward(net, X), xi64, mask.tolist(), pts.cpu().double(), lhs, rhs)
+    og = torch.autograd.grad(ol, net.tensors() + [xi64], allow_unused=True)
+    assert abs(float(loss.detach()) - float(ol.detach())) <= TOL * abs(float(ol.detach()))
+    assert rel_max(resid.cpu().numpy(), orr.detach().numpy()) <= TOL
+    got = np.concatenate([p.grad.cpu().numpy().ravel() for p in U.parameters()])
+    ref = np.concatenate([g.numpy().ravel() if g is not None else np.zeros(t.numel()) for g, t in zip(og[:-1], net.tensors())])
+    assert rel_max(got, ref) <= TOL
+    if K and og[-1] is not None and float(og[-1].abs().max()) > 0:
+        assert rel_max(xi.grad.cpu().numpy(), og[-1].numpy()) <= TOL
+
+
+def test_lbfgs_closure_reentry():
+    """Optimizer.step(Closure) with LBFGS calls the closure several times on the same points (Test_Train.py:193)."""
+    import pde_learn_b200 as P
+    from pde_learn_b200 import configs
+    torch.manual_seed(2)
+    d, bounds, derivs, lhs, rhs = configs.config("heat")
+    U = P.Network([2, 16, 16, 1], "Tanh", Device=_dev())
+    K = len(rhs)
+    Xi = torch.zeros(K, device=_dev(), requires_grad=True)
+    Mask = torch.zeros(K, dtype=torch.bool)
+    X = P.Generate_Points(bounds, 256, _dev(), Seed=1)
+    Y = (torch.sin(X[:, 0]) * torch.cos(X[:, 1])).double()
+    coll = P.Generate_Points(bounds, 1024, _dev(), Seed=2)
+    opt = torch.optim.LBFGS(list(U.parameters()) + [Xi], lr=0.5)
+    W = {"Data": 1.0, "Coll": 1.0, "Lp": 0.0, "L2": 1e-6}
+    first = P.Training([U], Xi, Mask, [coll], [X], [Y], derivs, lhs, rhs, 0.1, W, opt)
+    for _ in range(3):
+        last = P.Training([U], Xi, Mask, [coll], [X], [Y], derivs, lhs, rhs, 0.1, W, opt)
+    assert np.isfinite(last["Total Losses"][0]) and last["Total Losses"][0] < first["Total Losses"][0]
+    assert last["Residuals"][0].shape == (1024,)
