@@ -96,3 +96,54 @@ def test_run_epochs_two_networks_with_testing_and_device_sampler():
     assert h["Train Data"][-1].sum() < h["Train Data"][0].sum()          # it trains
     assert float(Xi.detach()[1]) == 0.0                                            # masked coefficient never moves
     assert (h["Num Targeted"] >= 0).all()
+
+
+SETTINGS = """
+Load U from Save [bool]:                         {load}
+Load Xi, Library from Save [bool]:               {load}
+Load Optimizer from Save [bool]:                 {load}
+    Load File Name [str]:                        {fname}
+Library File [str]:                              Library
+Hidden Layer Widths [List of int]:               20, 20, 20, 20, 20
+Hidden Activation Function [str]:                Tanh
+Train on CPU or GPU [GPU, CPU]:                  GPU
+p [float]:                                       .1
+Weights [Dict of float]:                         {{"Data" : 1.0, "Coll" : 1.0, "Lp" : {lp}, "L2" : 0.000005}}
+Number of Training Collocation Points [int]:     3000
+Number of Testing Collocation Points [int]:      1000
+Mask Small Xi Components [bool]:                 True
+Optimizer [Adam, LBFGS]:                         Adam
+Learning Rate [float]:                           .001
+Number of Epochs [int]:                          {epochs}
+DataSet Names [List of str]:                     [Burgers_Sine_N25_P2000]
+"""
+
+
+def test_main_driver_burn_in_then_resume(tmp_path):
+    """The reference's 2-stage workflow through `python -m pde_learn_b200.main`: burn-in run, save, resume with masking."""
+    import pde_learn_b200 as P
+    from pde_learn_b200 import configs
+    from pde_learn_b200.main import main
+    z = np.load(os.path.join(GOLDEN_DIR, "burgers_run.npz"))
+    (tmp_path / "Data" / "DataSets").mkdir(parents=True)
+    np.savez(tmp_path / "Data" / "DataSets" / "Burgers_Sine_N25_P2000.npz", Train_Inputs=z["inputs"], Train_Targets=z["targets"],
+             Test_Inputs=z["inputs"][:500], Test_Targets=z["targets"][:500], Input_Bounds=z["bounds"])
+    (tmp_path / "Library.txt").write_text("# shipped library\n" + configs.SHIPPED_LIBRARY)
+    st = tmp_path / "Settings.txt"
+    st.write_text(SETTINGS.format(load="False", fname="", lp="0.000", epochs=60))
+    out1 = main(["--settings", str(st), "--quiet"])
+    assert out1["History"]["Train Data"][-1, 0] < out1["History"]["Train Data"][0, 0]
+    assert out1["PDE"].startswith("(D_t U) = ") and os.path.isfile(tmp_path / "Saves" / out1["Save Name"])
+    xi1 = out1["Xi"].clone()
+    # stage 2: resume everything, mask the small coefficients, switch the Lp term on
+    st.write_text(SETTINGS.format(load="True", fname=out1["Save Name"], lp="0.0002", epochs=20))
+    out2 = main(["--settings", str(st), "--quiet"])
+    mask = out2["Mask"]
+    assert mask.tolist() == (xi1.abs() < 5e-4).tolist()
+    for k in range(len(mask)):
+        if mask[k]:
+            assert float(out2["Xi"][k]) == float(xi1[k])             # masked coefficients are restored, never trained
+    assert out2["Save Name"] != out1["Save Name"] and np.isfinite(out2["History"]["Train Total"]).all()
+    # the save file can be read back (and has the reference's keys)
+    blob = P.Load_State(str(tmp_path / "Saves" / out2["Save Name"]), torch.device("cuda", 0))
+    assert torch.equal(blob["Xi"].detach().cpu(), out2["Xi"]) and len(blob["RHS Terms"]) == 17
