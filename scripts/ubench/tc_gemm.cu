@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(128, 1) tc_kernel(const float* __restrict__ Ag
     const uint32_t tmem = S.tmem_base;
     uint32_t parity = 0;
     long long t0 = clock64();
-    const int reps = (mode == 3) ? iters : 1;
+    const int reps = (mode >= 3) ? iters : 1;
     for (int rep = 0; rep < reps; ++rep) {
         if (tid == 0) {
             if (mode == 2) {
@@ -120,6 +120,8 @@ __global__ void __launch_bounds__(128, 1) tc_kernel(const float* __restrict__ Ag
                 const uint32_t idesc = make_idesc(128, NP, 0, 0);
                 const int nsplit = (mode == 0) ? 1 : 3;
                 bool first = true;
+                const int batches = (mode == 4) ? 4 : 1;
+                for (int bt = 0; bt < batches; ++bt)
                 for (int ks = 0; ks < KP / 8; ++ks) {
                     for (int sp = 0; sp < nsplit; ++sp) {
                         const int ia = (sp == 2) ? 1 : 0, ib = (sp == 1) ? 1 : 0;   // hi*hi, hi*lo, lo*hi
@@ -225,6 +227,14 @@ int main() {
                                 ++hits;
                             }
         }
+    }
+    {
+        const int iters = 2000;
+        tc_kernel<<<sms, 128, smem>>>(dA, dB, dD, 4, iters, dC, dS);
+        cudaError_t e = cudaDeviceSynchronize();
+        cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost); cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost);
+        printf("mode 4: %s %s: 60 MMAs (4 layer contractions) per commit: %.1f cycles per commit = %.1f cycles/MMA; useful FMA/clk/SM = %.0f\n",
+               cudaGetErrorString(e), st ? "TIMED OUT" : "ok", (double)cyc / iters, (double)cyc / (60.0 * iters), 4.0 * 128 * 48 * 40 * iters / (double)cyc);
     }
     for (int iters : {2000}) {
         tc_kernel<<<sms, 128, smem>>>(dA, dB, dD, 3, iters, dC, dS);
