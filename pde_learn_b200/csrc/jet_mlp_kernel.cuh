@@ -799,13 +799,16 @@ void pdl_k_info(int* out) {
 // returns a cudaError_t
 int pdl_k_launch(const pdl::Params* P, int n_ctas, int bwd, float* grad_params, float* grad_xi, double* stats, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {false};          // the opt-in shared-memory size is a per-device function attribute
+    int dev = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 != cudaSuccess) return (int)e0;
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         cudaError_t e = cudaFuncSetAttribute(pdl_main_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pdl::SM_TOTAL * 4);
         if (e != cudaSuccess) return (int)e;
         e = cudaFuncSetAttribute(pdl_main_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pdl::SM_TOTAL * 4);
         if (e != cudaSuccess) return (int)e;
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     if (bwd) pdl_main_kernel<true><<<n_ctas, pdl::NT, pdl::SM_TOTAL * 4, st>>>(*P);
     else pdl_main_kernel<false><<<n_ctas, pdl::NT, pdl::SM_TOTAL * 4, st>>>(*P);
