@@ -1,23 +1,15 @@
-// jet_mlp_kernel.cuh -- fused jet-MLP + library-residual forward/adjoint kernel for sm_100a.
+// jet_mlp_kernel_mma.cuh -- fused jet-MLP + library-residual forward/adjoint kernel for sm_100a, tensor-pipe variant.
 //
-// Included at the END of a generated plan translation unit (see plan_codegen.cpp), which defines
-//   PDL_D, PDL_J, PDL_WP, PDL_H, PDL_K, PDL_ACT, PDL_NS, PDL_NW, PDL_MODE, PDL_SF, PDL_GS
-//   pdl_width(l), pdl_comp_axis(c), pdl_tanh_sigmas(), pdl_act_fwd(), pdl_act_adj(), pdl_epilogue()
+// Same contract, helpers and reductions as jet_mlp_kernel.cuh (see there for the reference map), but the two contractions
+// whose A operand is produced by the lane itself -- forward  z = W h  and data gradient  hb = zb W -- run as 3xTF32
+// mma.sync.m16n8k8 on the tensor pipe, concurrently with the FP32 pipe that keeps the jet activations, the weight gradient
+// and the epilogue.  A warp tile is 16 points (one m16 row block); lane = 4g + t owns points {g, g+8} and the neurons
+// {8j+2t, 8j+2t+1}: with the k index relabelled the same way, a lane's accumulator fragment of neuron tile j IS its A fragment
+// of k-step j, so activations never travel through shared memory between layers.  FP32-class accuracy comes from the split
+// x = hi + lo (hi = TF32 part): D += lo*Bhi + hi*Blo + hi*Bhi (measured 9e-7 relative, scripts/ubench/tc_gemm.cu).
 //
-// What it replaces in the reference (file:line under /root/reference):
-//   Network.forward                Code/Classes/Network.py:287-312     -> layer loop below (jets, not values)
-//   Derivative_From_Derivative     Code/Evaluate_Derivatives.py:20-207 -> forward jet propagation (no autograd)
-//   Coll_Loss                      Code/Loss.py:66-248                 -> pdl_epilogue + reductions
-//   Total.backward()               Code/Test_Train.py:187-188          -> hand-written adjoint (act_adj/dgrad/wgrad)
-//
-// Execution model: persistent grid, PDL_NW warps per CTA, every warp owns tiles of 8 collocation points.
-// lane = pg*4 + g4:  pg = point within the tile, g4 = group of NPL = WP/4 output neurons.
-// Weights live in shared memory (two layouts, one per GEMM direction); jets are exchanged between lanes
-// through per-warp shared buffers; pre-activation jets needed by the adjoint are parked in an L2-resident
-// per-warp scratch; weight-gradient partial sums live in a per-warp private buffer (no atomics).
-//
-// The same source compiles as plain C++ with -DPDL_EMULATE: every "per-lane" block becomes a loop over
-// 32 lanes and shuffles become array permutations.  That build is TEST INFRASTRUCTURE (tests/ only).
+// Included at the END of a generated plan translation unit when the plan compiler picks this engine (J <= 4).
+// The same source compiles as plain C++ with -DPDL_EMULATE (mma.sync is modelled lane-exactly): TEST INFRASTRUCTURE only.
 #pragma once
 #include <stdint.h>
 #include <math.h>
@@ -49,22 +41,25 @@ namespace pdl {
 
 constexpr int D = PDL_D, J = PDL_J, WP = PDL_WP, H = PDL_H, K = PDL_K, NS = PDL_NS, NW = PDL_NW;
 constexpr int KX = (K > 0) ? K : 1;
-constexpr int NPL = WP / 4;                 // neurons per lane group (fwd / dgrad micro-tile rows)
-constexpr int NPN = WP / 8;                 // neurons per lane group along n in wgrad
+constexpr int TP = 16;                      // points per warp tile: one m16 MMA row block
+constexpr int NT8 = WP / 8;                 // 8-wide neuron tiles (MMA n-tiles and k-steps)
+constexpr int NPL = WP / 4;                 // neurons per lane: 2 per neuron tile
+constexpr int NPN = WP / 8;                 // neurons per lane group along n in the weight gradient
+constexpr bool DGRAD_MMA = (PDL_DGRAD_MMA != 0);   // data gradient on the tensor pipe too (needs two more weight copies)
 constexpr int JA = (J >= 3) ? 4 : J;        // plane A width (comps 0..3)
 constexpr int JB = (J <= 4) ? 0 : ((J == 5) ? 1 : ((J == 6) ? 2 : ((J <= 8) ? 4 : 8)));   // plane B width (comps 4..)
 constexpr int pad_stride(int n) { int m = (n + 3) / 4 * 4; while (((m / 4) & 1) == 0) m += 4; return m; }
 constexpr int SA = pad_stride(WP * JA);     // floats per point in plane A (odd number of 16B chunks)
 constexpr int SB = (JB > 0) ? pad_stride(WP * JB) : 0;
-constexpr int SF = PDL_SF;                  // row stride of the forward weight copy  Wf[n][k]
-constexpr int GS = PDL_GS;                  // group stride of the dgrad weight copy  Wd[n][g4][i]
+constexpr int SF = WP;                      // row stride of the fragment-ordered weight copies (40: rows 8 banks apart)
+constexpr int GS = PDL_GS;                  // group stride of the FFMA dgrad weight copy  Wd[n][g4][i]
 constexpr int SD = 4 * GS;
 constexpr int NHH = (H > 1) ? (H - 1) : 0;  // hidden->hidden linear layers
 constexpr int NACC = NPN * NPL + NPN;       // wgrad accumulators per lane (weights + bias)
 constexpr int NACC4 = (NACC + 3) / 4 * 4;
 constexpr int WPRIV_LAYER = NACC4 * 32;     // floats per warp per hidden->hidden layer
 constexpr int WPRIV = NHH * WPRIV_LAYER;
-constexpr int ZS_LAYER = NPL * 32 * (JA + JB);
+constexpr int ZS_LAYER = 2 * NPL * 32 * (JA + JB);
 constexpr int ZSCR = NHH * ZS_LAYER;        // floats of pre-activation scratch per warp
 
 // small per-warp accumulators (shared memory), in floats
@@ -73,22 +68,28 @@ constexpr int SO_B0 = SO_W0 + WP * D;       // [WP]
 constexpr int SO_WH = SO_B0 + WP;           // [WP]
 constexpr int SO_BH = SO_WH + WP;           // [1]
 constexpr int SO_RAT = SO_BH + 1;           // [H][7]
-constexpr int SO_XI = SO_RAT + 7 * H;       // [KX][8] one slot per point-lane
-constexpr int SACC = (SO_XI + KX * 8 + 3) / 4 * 4;
+constexpr int SO_XI = SO_RAT + 7 * H;       // [KX][TP] one slot per point of the tile
+constexpr int SACC = (SO_XI + KX * TP + 3) / 4 * 4;
 constexpr int SACC_OUT = SO_XI + KX;        // what a CTA exports (xi slots summed)
 
 // shared-memory map (floats).  Shared part first, then NW private parts.
 constexpr int SM_W0 = 0;
 constexpr int SM_B0 = SM_W0 + WP * D;
-constexpr int SM_HH = (SM_B0 + WP + 3) / 4 * 4;              // per hidden->hidden layer: Wf, Wd, bias
-constexpr int HH_WF = 0, HH_WD = WP * SF, HH_B = HH_WD + WP * SD, HH_SIZE = (HH_B + WP + 3) / 4 * 4;
+constexpr int SM_HH = (SM_B0 + WP + 3) / 4 * 4;
+// per hidden->hidden layer: W hi/lo [n][k] (forward B fragments), then either W^T hi/lo [k][n] (dgrad B fragments)
+// or the FFMA dgrad copy Wd[n][g4][i]; bias
+constexpr int HH_WHI = 0, HH_WLO = WP * SF;
+constexpr int HH_THI = 2 * WP * SF, HH_TLO = 3 * WP * SF;
+constexpr int HH_WD = 2 * WP * SF;
+constexpr int HH_B = DGRAD_MMA ? 4 * WP * SF : (2 * WP * SF + WP * SD);
+constexpr int HH_SIZE = (HH_B + WP + 3) / 4 * 4;
 constexpr int SM_WH = SM_HH + NHH * HH_SIZE;
 constexpr int SM_BH = SM_WH + WP;
 constexpr int SM_RAT = (SM_BH + 1 + 3) / 4 * 4;              // [H][8]: a0..a3, b0..b2, pad
 constexpr int SM_XI = SM_RAT + 8 * H;                        // xi with masked entries zeroed
 constexpr int SM_GM = SM_XI + KX;                            // 1 - mask
 constexpr int SM_SHARED = (SM_GM + KX + 3) / 4 * 4;
-constexpr int BUF = (8 * (SA + SB) > 128) ? 8 * (SA + SB) : 128;   // also hosts 64 doubles at warp exit
+constexpr int BUF = (8 * (SA + SB) > 128) ? 8 * (SA + SB) : 128;   // 8 points at a time; also hosts 64 doubles at warp exit
 constexpr int SM_WARP = 2 * BUF + SACC;                      // bufH, bufZ, small accumulators
 constexpr int SM_TOTAL = SM_SHARED + NW * SM_WARP;
 constexpr int NT = NW * 32;
@@ -151,6 +152,7 @@ template <int W> PDL_DEV void stgw(float* p, const float* v) {
     else if (W == 2) { pdl_f2 a; a.x = v[0]; a.y = v[1]; stg2(p, a); }
     else if (W == 1) stg1(p, v[0]);
 }
+constexpr int ZS_ROWS = 2 * NPL;            // scratch rows per layer: (point half, local neuron)
 constexpr int JT = JA + JB;                 // padded component count (>= J)
 // one (point, neuron) entry of a jet buffer: comps 0..JA-1 in plane A, the rest in plane B
 PDL_DEV void load_entry(const float* A, const float* B, float (&v)[J]) {
@@ -173,12 +175,12 @@ PDL_DEV void scratch_store(float* zs, int slot, int i, int lane, const float (&v
 #pragma unroll
     for (int c = 0; c < JT; ++c) t[c] = (c < J) ? v[c < J ? c : 0] : 0.f;
     stgw<JA>(zs + slot * ZS_LAYER + (i * 32 + lane) * JA, t);
-    if (JB > 0) stgw<JB>(zs + slot * ZS_LAYER + NPL * 32 * JA + (i * 32 + lane) * JB, t + JA);
+    if (JB > 0) stgw<JB>(zs + slot * ZS_LAYER + ZS_ROWS * 32 * JA + (i * 32 + lane) * JB, t + JA);
 }
 PDL_DEV void scratch_load(const float* zs, int slot, int i, int lane, float (&v)[J]) {
     float t[JT];
     ldgw<JA>(zs + slot * ZS_LAYER + (i * 32 + lane) * JA, t);
-    if (JB > 0) ldgw<JB>(zs + slot * ZS_LAYER + NPL * 32 * JA + (i * 32 + lane) * JB, t + JA);
+    if (JB > 0) ldgw<JB>(zs + slot * ZS_LAYER + ZS_ROWS * 32 * JA + (i * 32 + lane) * JB, t + JA);
 #pragma unroll
     for (int c = 0; c < J; ++c) v[c] = t[c];
 }
@@ -195,6 +197,69 @@ PDL_DEV void xor_add(float (&v)[PDL_NL][N], int m) {
     for (int n = 0; n < N; ++n) v[0][n] += __shfl_xor_sync(0xffffffffu, v[0][n], m);
 #endif
 }
+
+// ---------------------------------------------------------------------------------------------
+// warp-level tensor-core step: D(16x8) += A(16x8) * B(8x8), TF32 inputs, FP32 accumulate (mma.sync.m16n8k8)
+//   lane = 4*g + t:  A: a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);  B: b0 (k=t, n=g) b1 (k=t+4, n=g);
+//                    C: c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+// Rows are the 16 points of the tile.  The k index is a summation index, so it is relabelled: slot t <-> neuron 8s+2t and
+// slot t+4 <-> neuron 8s+2t+1, which makes a lane's C fragment of neuron tile s exactly its A fragment of k-step s.
+// ---------------------------------------------------------------------------------------------
+PDL_DEV uint32_t f2u(float x) {
+#ifdef PDL_EMULATE
+    uint32_t u; memcpy(&u, &x, 4); return u;
+#else
+    return __float_as_uint(x);
+#endif
+}
+PDL_DEV float u2f(uint32_t u) {
+#ifdef PDL_EMULATE
+    float x; memcpy(&x, &u, 4); return x;
+#else
+    return __uint_as_float(u);
+#endif
+}
+// round-to-nearest (ties away) conversion FP32 -> TF32 bit pattern (low 13 mantissa bits zero)
+PDL_DEV uint32_t tf32_rna(float x) {
+#ifdef PDL_EMULATE
+    return (f2u(x) + 0x1000u) & 0xFFFFE000u;
+#else
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+#endif
+}
+// FP32 value -> (hi, lo): hi = TF32(x), lo = TF32(x - hi); x - hi is exact in FP32, so hi + lo carries ~22 mantissa bits
+PDL_DEV void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = tf32_rna(x);
+    lo = tf32_rna(x - u2f(hi));
+}
+PDL_DEV void warp_mma(float (&d)[PDL_NL][4], const uint32_t (&a)[PDL_NL][4], const uint32_t (&b)[PDL_NL][2]) {
+#ifdef PDL_EMULATE
+    float A[16][8], B[8][8];
+    for (int l = 0; l < 32; ++l) {
+        const int g = l >> 2, t = l & 3;
+        A[g][t] = u2f(a[l][0] & 0xFFFFE000u); A[g + 8][t] = u2f(a[l][1] & 0xFFFFE000u);
+        A[g][t + 4] = u2f(a[l][2] & 0xFFFFE000u); A[g + 8][t + 4] = u2f(a[l][3] & 0xFFFFE000u);
+        B[t][g] = u2f(b[l][0] & 0xFFFFE000u); B[t + 4][g] = u2f(b[l][1] & 0xFFFFE000u);
+    }
+    for (int l = 0; l < 32; ++l) {
+        const int g = l >> 2, t = l & 3;
+        for (int q = 0; q < 4; ++q) {
+            const int r = g + ((q & 2) ? 8 : 0), c = 2 * t + (q & 1);
+            float s = d[l][q];
+            for (int k = 0; k < 8; ++k) s += A[r][k] * B[k][c];
+            d[l][q] = s;
+        }
+    }
+#else
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0][0]), "+f"(d[0][1]), "+f"(d[0][2]), "+f"(d[0][3])
+                 : "r"(a[0][0]), "r"(a[0][1]), "r"(a[0][2]), "r"(a[0][3]), "r"(b[0][0]), "r"(b[0][1]));
+#endif
+}
+// neuron owned by lane-column t as element e (0/1) of neuron tile j, and its local index i = 2j + e
+PDL_DEV int own_neuron(int t, int i) { return 8 * (i >> 1) + 2 * t + (i & 1); }
 
 // ---------------------------------------------------------------------------------------------
 // activation sigmas: s[m] = sigma^(m)(z0), m = 0..NS-1
@@ -307,8 +372,18 @@ PDL_DEV void stage_thread2(const Params& P, float* sm, int tid) {
         for (int e = tid; e < wout * win; e += NT) {
             const int n = e / win, k = e - n * win;
             const float w = W[e];
-            base[HH_WF + n * SF + k] = w;
-            base[HH_WD + n * SD + (k / NPL) * GS + (k % NPL)] = w;
+            uint32_t uh, ul;
+            split_tf32(w, uh, ul);
+            const float hi = u2f(uh), lo = u2f(ul);
+            base[HH_WHI + n * SF + k] = hi;
+            base[HH_WLO + n * SF + k] = lo;
+            if (DGRAD_MMA) {
+                base[HH_THI + k * SF + n] = hi;
+                base[HH_TLO + k * SF + n] = lo;
+            } else {
+                // FFMA dgrad copy grouped by the lane column that owns input neuron k: t = (k%8)/2, i = 2*(k/8) + k%2
+                base[HH_WD + n * SD + ((k & 7) >> 1) * GS + 2 * (k >> 3) + (k & 1)] = w;
+            }
         }
         for (int e = tid; e < wout; e += NT) base[HH_B + e] = P.prm[2 * l + 1][e];
     }
@@ -332,6 +407,9 @@ PDL_DEV void stage_thread2(const Params& P, float* sm, int tid) {
 // ---------------------------------------------------------------------------------------------
 // the per-warp tile loop
 // ---------------------------------------------------------------------------------------------
+// element of a fragment array belonging to (point half pp, local neuron i): tile i>>1, register 2*pp + (i&1)
+#define PDL_FR(arr, i, c, pp) arr[(i) >> 1][c][PDL_L][2 * (pp) + ((i) & 1)]
+
 template <bool BWD>
 PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, int n_warps
 #ifndef PDL_EMULATE
@@ -343,215 +421,244 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
     float* sacc = bufZ + BUF;
     float* zs = BWD ? (P.zscratch + (size_t)gwarp * ZSCR) : nullptr;
     float* wp = BWD ? (P.wpriv + (size_t)gwarp * WPRIV) : nullptr;
-    const long long n_tiles = (P.n_points + 7) / 8;
+    const long long n_tiles = (P.n_points + TP - 1) / TP;
     const float two_inv_n = (float)(2.0 * P.inv_n);
 
     double lsum[PDL_NL], asum[PDL_NL];
     PDL_FOR_LANES { lsum[PDL_L] = 0.0; asum[PDL_L] = 0.0; }
 
-    float x[PDL_NL][D];
-    float h[PDL_NL][NPL][J];          // activation jets of the lane's neurons (layer being produced)
-    float hb[PDL_NL][NPL][J];         // adjoint jets flowing backwards
-    float uu[PDL_NL][J];
-    float ub[PDL_NL][J];
-    float valid[PDL_NL];
+    float x[PDL_NL][2][D];
+    float hf[NT8][J][PDL_NL][4];      // activation jets as C/A fragments: [neuron tile][component][lane][2*pp + e]
+    float hbf[NT8][J][PDL_NL][4];     // adjoint jets flowing backwards, same layout
+    float uu[PDL_NL][2 * J];
+    float ub[PDL_NL][2][J];
     bool first = true;
 
     for (long long tile = gwarp; tile < n_tiles; tile += n_warps, first = false) {
-        // ---------------- layer 0 forward ----------------
+        // ---------------- layer 0 forward (CUDA cores: K = d is tiny) ----------------
         PDL_FOR_LANES {
-            const int pg = lane >> 2, g4 = lane & 3;
-            const long long p = tile * 8 + pg;
-            valid[PDL_L] = (p < P.n_points) ? 1.f : 0.f;
+            const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-            for (int dd = 0; dd < D; ++dd) x[PDL_L][dd] = (p < P.n_points) ? P.points[p * D + dd] : 0.f;
+            for (int pp = 0; pp < 2; ++pp) {
+                const long long p = tile * TP + g + 8 * pp;
 #pragma unroll
-            for (int i = 0; i < NPL; ++i) {
-                const int n = g4 * NPL + i;
-                float z[J];
-                layer0_preact(sm, n, x[PDL_L], z);
-                act_forward(z, sm + SM_RAT, h[PDL_L][i]);
-                store_entry(bufH + pg * SA + n * JA, bufH + 8 * SA + pg * SB + n * JB, h[PDL_L][i]);
+                for (int dd = 0; dd < D; ++dd) x[PDL_L][pp][dd] = (p < P.n_points) ? P.points[p * D + dd] : 0.f;
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) {
+                    float z[J], hv[J];
+                    layer0_preact(sm, own_neuron(t, i), x[PDL_L][pp], z);
+                    act_forward(z, sm + SM_RAT, hv);
+#pragma unroll
+                    for (int c = 0; c < J; ++c) PDL_FR(hf, i, c, pp) = hv[c];
+                }
             }
         }
-        PDL_SYNCWARP();
-        // ---------------- hidden -> hidden layers, forward ----------------
+        // ---------------- hidden -> hidden layers, forward: 3xTF32 on the tensor pipe ----------------
         for (int l = 1; l < H; ++l) {
-            const float* Wf = sm + SM_HH + (l - 1) * HH_SIZE + HH_WF;
+            const float* Whi = sm + SM_HH + (l - 1) * HH_SIZE + HH_WHI;
+            const float* Wlo = sm + SM_HH + (l - 1) * HH_SIZE + HH_WLO;
             const float* bl = sm + SM_HH + (l - 1) * HH_SIZE + HH_B;
+            float acc[NT8][J][PDL_NL][4];
             PDL_FOR_LANES {
-                const int pg = lane >> 2, g4 = lane & 3;
-                float acc[NPL][J];
+                const int t = lane & 3;
 #pragma unroll
-                for (int i = 0; i < NPL; ++i) {
-                    acc[i][0] = bl[g4 * NPL + i];
+                for (int q = 0; q < NT8; ++q) {
+                    const float b0 = bl[8 * q + 2 * t], b1 = bl[8 * q + 2 * t + 1];
+                    acc[q][0][PDL_L][0] = b0; acc[q][0][PDL_L][1] = b1; acc[q][0][PDL_L][2] = b0; acc[q][0][PDL_L][3] = b1;
 #pragma unroll
-                    for (int c = 1; c < J; ++c) acc[i][c] = 0.f;
-                }
-                const float* hA = bufH + pg * SA;
-                const float* hB = bufH + 8 * SA + pg * SB;
-                const float* wrow = Wf + (g4 * NPL) * SF;
-#pragma unroll 2
-                for (int kc = 0; kc < WP; kc += 4) {
-                    float a[4][J];
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) load_entry(hA + (kc + kk) * JA, hB + (kc + kk) * JB, a[kk]);
-#pragma unroll
-                    for (int i = 0; i < NPL; ++i) {
-                        const pdl_f4 w = ld4(wrow + i * SF + kc);
-#pragma unroll
-                        for (int c = 0; c < J; ++c) {
-                            acc[i][c] += a[0][c] * w.x;
-                            acc[i][c] += a[1][c] * w.y;
-                            acc[i][c] += a[2][c] * w.z;
-                            acc[i][c] += a[3][c] * w.w;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < NPL; ++i) {
-                    if (BWD) scratch_store(zs, l - 1, i, lane, acc[i]);
-                    act_forward(acc[i], sm + SM_RAT + l * 8, h[PDL_L][i]);
+                    for (int c = 1; c < J; ++c) { acc[q][c][PDL_L][0] = 0.f; acc[q][c][PDL_L][1] = 0.f; acc[q][c][PDL_L][2] = 0.f; acc[q][c][PDL_L][3] = 0.f; }
                 }
             }
-            PDL_SYNCWARP();
-            if (l < H - 1) {                 // the last hidden layer feeds the output layer from registers
-                PDL_FOR_LANES {
-                    const int pg = lane >> 2, g4 = lane & 3;
 #pragma unroll
-                    for (int i = 0; i < NPL; ++i) {
-                        const int n = g4 * NPL + i;
-                        store_entry(bufH + pg * SA + n * JA, bufH + 8 * SA + pg * SB + n * JB, h[PDL_L][i]);
+            for (int s = 0; s < NT8; ++s) {
+                uint32_t ahi[J][PDL_NL][4], alo[J][PDL_NL][4];
+                PDL_FOR_LANES {
+#pragma unroll
+                    for (int c = 0; c < J; ++c) {
+                        split_tf32(hf[s][c][PDL_L][0], ahi[c][PDL_L][0], alo[c][PDL_L][0]);
+                        split_tf32(hf[s][c][PDL_L][2], ahi[c][PDL_L][1], alo[c][PDL_L][1]);
+                        split_tf32(hf[s][c][PDL_L][1], ahi[c][PDL_L][2], alo[c][PDL_L][2]);
+                        split_tf32(hf[s][c][PDL_L][3], ahi[c][PDL_L][3], alo[c][PDL_L][3]);
                     }
                 }
-                PDL_SYNCWARP();
+#pragma unroll
+                for (int q = 0; q < NT8; ++q) {
+                    uint32_t bhi[PDL_NL][2], blo[PDL_NL][2];
+                    PDL_FOR_LANES {
+                        const int g = lane >> 2, t = lane & 3;
+                        const pdl_f2 vh = ld2(Whi + (8 * q + g) * SF + 8 * s + 2 * t);
+                        const pdl_f2 vl = ld2(Wlo + (8 * q + g) * SF + 8 * s + 2 * t);
+                        bhi[PDL_L][0] = f2u(vh.x); bhi[PDL_L][1] = f2u(vh.y); blo[PDL_L][0] = f2u(vl.x); blo[PDL_L][1] = f2u(vl.y);
+                    }
+#pragma unroll
+                    for (int c = 0; c < J; ++c) {
+                        warp_mma(acc[q][c], alo[c], bhi);
+                        warp_mma(acc[q][c], ahi[c], blo);
+                        warp_mma(acc[q][c], ahi[c], bhi);
+                    }
+                }
+            }
+            PDL_FOR_LANES {
+#pragma unroll
+                for (int pp = 0; pp < 2; ++pp) {
+#pragma unroll
+                    for (int i = 0; i < NPL; ++i) {
+                        float z[J], hv[J];
+#pragma unroll
+                        for (int c = 0; c < J; ++c) z[c] = PDL_FR(acc, i, c, pp);
+                        if (BWD) scratch_store(zs, l - 1, pp * NPL + i, lane, z);
+                        act_forward(z, sm + SM_RAT + l * 8, hv);
+#pragma unroll
+                        for (int c = 0; c < J; ++c) PDL_FR(hf, i, c, pp) = hv[c];
+                    }
+                }
             }
         }
         // ---------------- output layer (identity activation) ----------------
         PDL_FOR_LANES {
-            const int g4 = lane & 3;
+            const int t = lane & 3;
 #pragma unroll
-            for (int c = 0; c < J; ++c) uu[PDL_L][c] = 0.f;
+            for (int q = 0; q < 2 * J; ++q) uu[PDL_L][q] = 0.f;
 #pragma unroll
             for (int i = 0; i < NPL; ++i) {
-                const float w = sm[SM_WH + g4 * NPL + i];
+                const float w = sm[SM_WH + own_neuron(t, i)];
 #pragma unroll
-                for (int c = 0; c < J; ++c) uu[PDL_L][c] += w * h[PDL_L][i][c];
+                for (int pp = 0; pp < 2; ++pp) {
+#pragma unroll
+                    for (int c = 0; c < J; ++c) uu[PDL_L][pp * J + c] += w * PDL_FR(hf, i, c, pp);
+                }
             }
         }
-        xor_add<J>(uu, 1);
-        xor_add<J>(uu, 2);
+        xor_add<2 * J>(uu, 1);
+        xor_add<2 * J>(uu, 2);
         // ---------------- library terms, residual, loss, seeds ----------------
         PDL_FOR_LANES {
-            const int pg = lane >> 2, g4 = lane & 3;
-            const long long p = tile * 8 + pg;
-            float u[J];
+            const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-            for (int c = 0; c < J; ++c) u[c] = uu[PDL_L][c];
-            u[0] += sm[SM_BH];
-            float r, du[J], T[KX];
-            pdl_epilogue(u, sm + SM_XI, r, du, T);
-            double rd = (double)r;
+            for (int pp = 0; pp < 2; ++pp) {
+                const int pt = g + 8 * pp;
+                const long long p = tile * TP + pt;
+                const bool ok = p < P.n_points;
+                float u[J];
+#pragma unroll
+                for (int c = 0; c < J; ++c) u[c] = uu[PDL_L][pp * J + c];
+                u[0] += sm[SM_BH];
+                float r, du[J], T[KX];
+                pdl_epilogue(u, sm + SM_XI, r, du, T);
+                double rd = (double)r;
 #if PDL_MODE == 1
-            rd = (p < P.n_points) ? ((double)r - P.targets[p]) : 0.0;      // f32 prediction - f64 target (Loss.py:56-59)
-            r = (float)rd;
+                rd = ok ? ((double)r - P.targets[p]) : 0.0;      // f32 prediction - f64 target (Loss.py:56-59)
+                r = (float)rd;
 #endif
-            const float v = valid[PDL_L];
-            if (g4 == 0 && v != 0.f) {
-                if (P.residual) P.residual[p] = r;
-                if (P.features) {
+                if (t == 0 && ok) {
+                    if (P.residual) P.residual[p] = r;
+                    if (P.features) {
 #pragma unroll
-                    for (int c = 0; c < J; ++c) P.features[(size_t)c * P.n_points + p] = u[c];
+                        for (int c = 0; c < J; ++c) P.features[(size_t)c * P.n_points + p] = u[c];
+                    }
+                    lsum[PDL_L] += rd * rd;
+                    asum[PDL_L] += fabs(rd);
                 }
-                lsum[PDL_L] += rd * rd;
-                asum[PDL_L] += fabs(rd);
-            }
-            if (BWD) {
+                if (BWD) {
 #if PDL_MODE == 1
-                const float rs = (float)(2.0 * P.inv_n * rd) * v;
+                    const float rs = ok ? (float)(2.0 * P.inv_n * rd) : 0.f;
 #else
-                const float rs = two_inv_n * r * v;
+                    const float rs = ok ? two_inv_n * r : 0.f;
 #endif
 #pragma unroll
-                for (int c = 0; c < J; ++c) ub[PDL_L][c] = rs * du[c];
-                if (g4 == 0) {
+                    for (int c = 0; c < J; ++c) ub[PDL_L][pp][c] = rs * du[c];
+                    if (t == 0) {
 #pragma unroll
-                    for (int k = 0; k < K; ++k) sacc[SO_XI + k * 8 + pg] -= rs * T[k] * sm[SM_GM + k];
+                        for (int k = 0; k < K; ++k) sacc[SO_XI + k * TP + pt] -= rs * T[k] * sm[SM_GM + k];
+                    }
                 }
             }
         }
         if (!BWD) continue;
         // ---------------- output layer adjoint ----------------
         {
-            float g[PDL_NL][NPL + 1];
+            float gw[PDL_NL][NPL + 1];
             PDL_FOR_LANES {
-                const int g4 = lane & 3;
+                const int t = lane & 3;
 #pragma unroll
                 for (int i = 0; i < NPL; ++i) {
-                    float t = 0.f;
+                    const float w = sm[SM_WH + own_neuron(t, i)];
+                    float a = 0.f;
 #pragma unroll
-                    for (int c = 0; c < J; ++c) t += ub[PDL_L][c] * h[PDL_L][i][c];
-                    g[PDL_L][i] = t;
-                    const float w = sm[SM_WH + g4 * NPL + i];
+                    for (int pp = 0; pp < 2; ++pp) {
 #pragma unroll
-                    for (int c = 0; c < J; ++c) hb[PDL_L][i][c] = w * ub[PDL_L][c];
+                        for (int c = 0; c < J; ++c) {
+                            a += ub[PDL_L][pp][c] * PDL_FR(hf, i, c, pp);
+                            PDL_FR(hbf, i, c, pp) = w * ub[PDL_L][pp][c];
+                        }
+                    }
+                    gw[PDL_L][i] = a;
                 }
-                g[PDL_L][NPL] = ub[PDL_L][0];
+                gw[PDL_L][NPL] = ub[PDL_L][0][0] + ub[PDL_L][1][0];
             }
-            xor_add<NPL + 1>(g, 4); xor_add<NPL + 1>(g, 8); xor_add<NPL + 1>(g, 16);
+            xor_add<NPL + 1>(gw, 4); xor_add<NPL + 1>(gw, 8); xor_add<NPL + 1>(gw, 16);
             PDL_FOR_LANES {
-                const int pg = lane >> 2, g4 = lane & 3;
-                if (pg == 0) {
+                const int g = lane >> 2, t = lane & 3;
+                if (g == 0) {
 #pragma unroll
-                    for (int i = 0; i < NPL; ++i) sacc[SO_WH + g4 * NPL + i] += g[PDL_L][i];
-                    if (g4 == 0) sacc[SO_BH] += g[PDL_L][NPL];
+                    for (int i = 0; i < NPL; ++i) sacc[SO_WH + own_neuron(t, i)] += gw[PDL_L][i];
+                    if (t == 0) sacc[SO_BH] += gw[PDL_L][NPL];
                 }
             }
         }
         // ---------------- hidden -> hidden layers, adjoint ----------------
         for (int l = H - 1; l >= 1; --l) {
+            float zbf[NT8][J][PDL_NL][4];             // adjoint of the pre-activations, kept as A fragments for the dgrad MMAs
+            float wacc[PDL_NL][NACC4];                // weight-gradient register tile (NPN x NPL + bias), v1 lane mapping
             float ga[PDL_NL][7];
+            float* wpl = wp + (l - 1) * WPRIV_LAYER;
             PDL_FOR_LANES {
-                const int pg = lane >> 2, g4 = lane & 3;
 #pragma unroll
                 for (int q = 0; q < 7; ++q) ga[PDL_L][q] = 0.f;
+                if (first) {
 #pragma unroll
-                for (int i = 0; i < NPL; ++i) {
-                    const int n = g4 * NPL + i;
-                    float z[J], zb[J];
-                    scratch_load(zs, l - 1, i, lane, z);
-                    act_adjoint(z, hb[PDL_L][i], sm + SM_RAT + l * 8, zb, ga[PDL_L]);
-                    store_entry(bufZ + pg * SA + n * JA, bufZ + 8 * SA + pg * SB + n * JB, zb);
-                    // activations of the layer below (input of this linear layer), recomputed
-                    float zi[J], hi[J];
-                    if (l >= 2) scratch_load(zs, l - 2, i, lane, zi);
-                    else layer0_preact(sm, n, x[PDL_L], zi);
-                    act_forward(zi, sm + SM_RAT + (l - 1) * 8, hi);
-                    store_entry(bufH + pg * SA + n * JA, bufH + 8 * SA + pg * SB + n * JB, hi);
+                    for (int a = 0; a < NACC4; ++a) wacc[PDL_L][a] = 0.f;
+                } else {
+#pragma unroll
+                    for (int a = 0; a < NACC4; a += 4) {
+                        const pdl_f4 v = ldg4(wpl + (a / 4 * 32 + lane) * 4);
+                        wacc[PDL_L][a] = v.x; wacc[PDL_L][a + 1] = v.y; wacc[PDL_L][a + 2] = v.z; wacc[PDL_L][a + 3] = v.w;
+                    }
                 }
             }
-            PDL_SYNCWARP();
-#if PDL_ACT == 1
-            xor_add<7>(ga, 1); xor_add<7>(ga, 2); xor_add<7>(ga, 4); xor_add<7>(ga, 8); xor_add<7>(ga, 16);
-            PDL_FOR_LANES { if (lane == 0) { for (int q = 0; q < 7; ++q) sacc[SO_RAT + l * 7 + q] += ga[PDL_L][q]; } }
-#endif
-            const float* Wd = sm + SM_HH + (l - 1) * HH_SIZE + HH_WD;
-            PDL_FOR_LANES {
-                const int pg = lane >> 2, g4 = lane & 3, g8 = lane >> 2;
-                // ---- weight gradient: Wbar[n][k] += sum_p sum_c zb[p][n][c] * h[p][k][c]   (n in g8 group, k in g4 group)
-                {
-                    float acc[NACC4];
-                    float* wpl = wp + (l - 1) * WPRIV_LAYER;
-                    if (first) {
+#pragma unroll 1
+            for (int pp = 0; pp < 2; ++pp) {
+                PDL_FOR_LANES {
+                    const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-                        for (int a = 0; a < NACC4; ++a) acc[a] = 0.f;
-                    } else {
+                    for (int i = 0; i < NPL; ++i) {
+                        const int n = own_neuron(t, i);
+                        float z[J], zb[J], hbv[J];
+                        scratch_load(zs, l - 1, pp * NPL + i, lane, z);
 #pragma unroll
-                        for (int a = 0; a < NACC4; a += 4) {
-                            const pdl_f4 t = ldg4(wpl + (a / 4 * 32 + lane) * 4);
-                            acc[a] = t.x; acc[a + 1] = t.y; acc[a + 2] = t.z; acc[a + 3] = t.w;
+                        for (int c = 0; c < J; ++c) hbv[c] = (pp == 0) ? PDL_FR(hbf, i, c, 0) : PDL_FR(hbf, i, c, 1);
+                        act_adjoint(z, hbv, sm + SM_RAT + l * 8, zb, ga[PDL_L]);
+#pragma unroll
+                        for (int c = 0; c < J; ++c) { if (pp == 0) PDL_FR(zbf, i, c, 0) = zb[c]; else PDL_FR(zbf, i, c, 1) = zb[c]; }
+                        store_entry(bufZ + g * SA + n * JA, bufZ + 8 * SA + g * SB + n * JB, zb);
+                        // activations of the layer below (input of this linear layer), recomputed
+                        float zi[J], hi[J];
+                        if (l >= 2) scratch_load(zs, l - 2, pp * NPL + i, lane, zi);
+                        else {
+                            float xp[D];
+#pragma unroll
+                            for (int dd = 0; dd < D; ++dd) xp[dd] = (pp == 0) ? x[PDL_L][0][dd] : x[PDL_L][1][dd];
+                            layer0_preact(sm, n, xp, zi);
                         }
+                        act_forward(zi, sm + SM_RAT + (l - 1) * 8, hi);
+                        store_entry(bufH + g * SA + n * JA, bufH + 8 * SA + g * SB + n * JB, hi);
                     }
+                }
+                PDL_SYNCWARP();
+                const float* Wd = sm + SM_HH + (l - 1) * HH_SIZE + HH_WD;
+                PDL_FOR_LANES {
+                    const int g = lane >> 2, g4 = lane & 3, g8 = lane >> 2;
+                    // ---- weight gradient over the 8 points in the buffers (FP32 pipe): Wbar[n][k] += sum_c zb[p][n][c] h[p][k][c]
 #pragma unroll 2
                     for (int q = 0; q < 8; ++q) {
                         float zq[NPN][J], hq[NPL][J];
@@ -564,70 +671,130 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
 #pragma unroll
                             for (int b = 0; b < NPL; ++b) {
 #pragma unroll
-                                for (int c = 0; c < J; ++c) acc[a * NPL + b] += zq[a][c] * hq[b][c];
+                                for (int c = 0; c < J; ++c) wacc[PDL_L][a * NPL + b] += zq[a][c] * hq[b][c];
                             }
-                            acc[NPN * NPL + a] += zq[a][0];
+                            wacc[PDL_L][NPN * NPL + a] += zq[a][0];
                         }
                     }
-#pragma unroll
-                    for (int a = 0; a < NACC4; a += 4) {
-                        pdl_f4 t; t.x = acc[a]; t.y = acc[a + 1]; t.z = acc[a + 2]; t.w = acc[a + 3];
-                        stg4(wpl + (a / 4 * 32 + lane) * 4, t);
-                    }
-                }
-                // ---- data gradient: hb[p][k] = sum_n zb[p][n] * W[n][k]   (k in own group)
-#pragma unroll
-                for (int i = 0; i < NPL; ++i) {
-#pragma unroll
-                    for (int c = 0; c < J; ++c) hb[PDL_L][i][c] = 0.f;
-                }
-                const float* zA = bufZ + pg * SA;
-                const float* zB = bufZ + 8 * SA + pg * SB;
-#pragma unroll 2
-                for (int nc = 0; nc < WP; nc += 4) {
-                    float a[4][J];
-#pragma unroll
-                    for (int nn = 0; nn < 4; ++nn) load_entry(zA + (nc + nn) * JA, zB + (nc + nn) * JB, a[nn]);
-#pragma unroll
-                    for (int nn = 0; nn < 4; ++nn) {
-                        const float* wr = Wd + (nc + nn) * SD + g4 * GS;
-                        float w[NPL];
-#pragma unroll
-                        for (int i = 0; i + 3 < NPL; i += 4) { const pdl_f4 t = ld4(wr + i); w[i] = t.x; w[i + 1] = t.y; w[i + 2] = t.z; w[i + 3] = t.w; }
-                        if ((NPL & 3) >= 2) { const pdl_f2 t = ld2(wr + (NPL & ~3)); w[(NPL & ~3)] = t.x; w[(NPL & ~3) + 1 < NPL ? (NPL & ~3) + 1 : 0] = t.y; }
-                        if (NPL & 1) w[NPL - 1] = wr[NPL - 1];
+                    if (!DGRAD_MMA) {
+                        // ---- data gradient on the FP32 pipe for this half: hb[p][k] = sum_n zb[p][n] W[n][k], k = own_neuron(t, i)
+                        float hacc[NPL][J];
 #pragma unroll
                         for (int i = 0; i < NPL; ++i) {
 #pragma unroll
-                            for (int c = 0; c < J; ++c) hb[PDL_L][i][c] += a[nn][c] * w[i];
+                            for (int c = 0; c < J; ++c) hacc[i][c] = 0.f;
+                        }
+                        const float* zA = bufZ + g * SA;
+                        const float* zB = bufZ + 8 * SA + g * SB;
+#pragma unroll 2
+                        for (int nc = 0; nc < WP; nc += 4) {
+                            float a[4][J];
+#pragma unroll
+                            for (int nn = 0; nn < 4; ++nn) load_entry(zA + (nc + nn) * JA, zB + (nc + nn) * JB, a[nn]);
+#pragma unroll
+                            for (int nn = 0; nn < 4; ++nn) {
+                                const float* wr = Wd + (nc + nn) * SD + g4 * GS;
+                                float w[NPL];
+#pragma unroll
+                                for (int i = 0; i + 3 < NPL; i += 4) { const pdl_f4 v = ld4(wr + i); w[i] = v.x; w[i + 1] = v.y; w[i + 2] = v.z; w[i + 3] = v.w; }
+                                if ((NPL & 3) >= 2) { const pdl_f2 v = ld2(wr + (NPL & ~3)); w[(NPL & ~3)] = v.x; w[(NPL & ~3) + 1 < NPL ? (NPL & ~3) + 1 : 0] = v.y; }
+#pragma unroll
+                                for (int i = 0; i < NPL; ++i) {
+#pragma unroll
+                                    for (int c = 0; c < J; ++c) hacc[i][c] += a[nn][c] * w[i];
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < NPL; ++i) {
+#pragma unroll
+                            for (int c = 0; c < J; ++c) { if (pp == 0) PDL_FR(hbf, i, c, 0) = hacc[i][c]; else PDL_FR(hbf, i, c, 1) = hacc[i][c]; }
+                        }
+                    }
+                }
+                PDL_SYNCWARP();
+            }
+            PDL_FOR_LANES {
+#pragma unroll
+                for (int a = 0; a < NACC4; a += 4) {
+                    pdl_f4 v; v.x = wacc[PDL_L][a]; v.y = wacc[PDL_L][a + 1]; v.z = wacc[PDL_L][a + 2]; v.w = wacc[PDL_L][a + 3];
+                    stg4(wpl + (a / 4 * 32 + lane) * 4, v);
+                }
+            }
+#if PDL_ACT == 1
+            xor_add<7>(ga, 1); xor_add<7>(ga, 2); xor_add<7>(ga, 4); xor_add<7>(ga, 8); xor_add<7>(ga, 16);
+            PDL_FOR_LANES { if (lane == 0) { for (int q = 0; q < 7; ++q) sacc[SO_RAT + l * 7 + q] += ga[PDL_L][q]; } }
+#endif
+            if (DGRAD_MMA) {
+                // ---- data gradient on the tensor pipe: hb = zb W, A fragments straight from the registers
+                const float* Thi = sm + SM_HH + (l - 1) * HH_SIZE + HH_THI;
+                const float* Tlo = sm + SM_HH + (l - 1) * HH_SIZE + HH_TLO;
+                PDL_FOR_LANES {
+#pragma unroll
+                    for (int q = 0; q < NT8; ++q) {
+#pragma unroll
+                        for (int c = 0; c < J; ++c) { hbf[q][c][PDL_L][0] = 0.f; hbf[q][c][PDL_L][1] = 0.f; hbf[q][c][PDL_L][2] = 0.f; hbf[q][c][PDL_L][3] = 0.f; }
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < NT8; ++s) {
+                    uint32_t ahi[J][PDL_NL][4], alo[J][PDL_NL][4];
+                    PDL_FOR_LANES {
+#pragma unroll
+                        for (int c = 0; c < J; ++c) {
+                            split_tf32(zbf[s][c][PDL_L][0], ahi[c][PDL_L][0], alo[c][PDL_L][0]);
+                            split_tf32(zbf[s][c][PDL_L][2], ahi[c][PDL_L][1], alo[c][PDL_L][1]);
+                            split_tf32(zbf[s][c][PDL_L][1], ahi[c][PDL_L][2], alo[c][PDL_L][2]);
+                            split_tf32(zbf[s][c][PDL_L][3], ahi[c][PDL_L][3], alo[c][PDL_L][3]);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < NT8; ++q) {
+                        uint32_t bhi[PDL_NL][2], blo[PDL_NL][2];
+                        PDL_FOR_LANES {
+                            const int g = lane >> 2, t = lane & 3;
+                            const pdl_f2 vh = ld2(Thi + (8 * q + g) * SF + 8 * s + 2 * t);
+                            const pdl_f2 vl = ld2(Tlo + (8 * q + g) * SF + 8 * s + 2 * t);
+                            bhi[PDL_L][0] = f2u(vh.x); bhi[PDL_L][1] = f2u(vh.y); blo[PDL_L][0] = f2u(vl.x); blo[PDL_L][1] = f2u(vl.y);
+                        }
+#pragma unroll
+                        for (int c = 0; c < J; ++c) {
+                            warp_mma(hbf[q][c], alo[c], bhi);
+                            warp_mma(hbf[q][c], ahi[c], blo);
+                            warp_mma(hbf[q][c], ahi[c], bhi);
                         }
                     }
                 }
             }
-            PDL_SYNCWARP();
         }
         // ---------------- layer 0 adjoint ----------------
         {
             float g0[PDL_NL][NPL * (D + 1)];
             float ga[PDL_NL][7];
             PDL_FOR_LANES {
-                const int g4 = lane & 3;
+                const int t = lane & 3;
 #pragma unroll
                 for (int q = 0; q < 7; ++q) ga[PDL_L][q] = 0.f;
 #pragma unroll
-                for (int i = 0; i < NPL; ++i) {
-                    const int n = g4 * NPL + i;
-                    float z[J], zb[J];
-                    layer0_preact(sm, n, x[PDL_L], z);
-                    act_adjoint(z, hb[PDL_L][i], sm + SM_RAT, zb, ga[PDL_L]);
+                for (int q = 0; q < NPL * (D + 1); ++q) g0[PDL_L][q] = 0.f;
 #pragma unroll
-                    for (int dd = 0; dd < D; ++dd) {
-                        float t = zb[0] * x[PDL_L][dd];
+                for (int pp = 0; pp < 2; ++pp) {
 #pragma unroll
-                        for (int c = 1; c < J; ++c) if (pdl_comp_axis(c) == dd) t += zb[c];
-                        g0[PDL_L][i * (D + 1) + dd] = t;
+                    for (int i = 0; i < NPL; ++i) {
+                        float z[J], zb[J], hbv[J];
+                        layer0_preact(sm, own_neuron(t, i), x[PDL_L][pp], z);
+#pragma unroll
+                        for (int c = 0; c < J; ++c) hbv[c] = PDL_FR(hbf, i, c, pp);
+                        act_adjoint(z, hbv, sm + SM_RAT, zb, ga[PDL_L]);
+#pragma unroll
+                        for (int dd = 0; dd < D; ++dd) {
+                            float a = zb[0] * x[PDL_L][pp][dd];
+#pragma unroll
+                            for (int c = 1; c < J; ++c) if (pdl_comp_axis(c) == dd) a += zb[c];
+                            g0[PDL_L][i * (D + 1) + dd] += a;
+                        }
+                        g0[PDL_L][i * (D + 1) + D] += zb[0];
                     }
-                    g0[PDL_L][i * (D + 1) + D] = zb[0];
                 }
             }
             xor_add<NPL*(D + 1)>(g0, 4); xor_add<NPL*(D + 1)>(g0, 8); xor_add<NPL*(D + 1)>(g0, 16);
@@ -635,11 +802,11 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
             xor_add<7>(ga, 1); xor_add<7>(ga, 2); xor_add<7>(ga, 4); xor_add<7>(ga, 8); xor_add<7>(ga, 16);
 #endif
             PDL_FOR_LANES {
-                const int pg = lane >> 2, g4 = lane & 3;
-                if (pg == 0) {
+                const int g = lane >> 2, t = lane & 3;
+                if (g == 0) {
 #pragma unroll
                     for (int i = 0; i < NPL; ++i) {
-                        const int n = g4 * NPL + i;
+                        const int n = own_neuron(t, i);
 #pragma unroll
                         for (int dd = 0; dd < D; ++dd) sacc[SO_W0 + n * D + dd] += g0[PDL_L][i * (D + 1) + dd];
                         sacc[SO_B0 + n] += g0[PDL_L][i * (D + 1) + D];
@@ -653,7 +820,7 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
         PDL_SYNCWARP();
     }
 
-    // ---- warp epilogue: a warp that never ran a tile must still publish zeros; loss partials via shuffles ----
+    // ---- warp epilogue: a warp that never ran a tile must still publish zeros ----
     if (BWD && first) {
         PDL_FOR_LANES {
             pdl_f4 zero; zero.x = zero.y = zero.z = zero.w = 0.f;
@@ -685,7 +852,7 @@ PDL_DEV void cta_tail_thread(const Params& P, const float* sm, int cta, int tid,
             for (int w = 0; w < NW; ++w) {
                 const float* sacc = sm + SM_SHARED + w * SM_WARP + 2 * BUF;
                 if (e < SO_XI) s += sacc[e];
-                else { const int k = e - SO_XI; for (int q = 0; q < 8; ++q) s += sacc[SO_XI + k * 8 + q]; }
+                else { const int k = e - SO_XI; for (int q = 0; q < TP; ++q) s += sacc[SO_XI + k * TP + q]; }
             }
             out[WPRIV + e] = s;
         }
@@ -794,7 +961,7 @@ void pdl_k_info(int* out) {
     out[0] = pdl::SM_TOTAL * 4; out[1] = pdl::NT; out[2] = pdl::ZSCR; out[3] = pdl::WPRIV; out[4] = pdl::CTA_OUT;
     out[5] = pdl::NPRM; out[6] = pdl::J; out[7] = pdl::K; out[8] = pdl::D; out[9] = pdl::NW;
     int np = 0; for (int t = 0; t < pdl::NPRM; ++t) np = pdl::prm_offset(t + 1); out[10] = np;
-    out[11] = PDL_MODE; out[12] = 8;
+    out[11] = PDL_MODE; out[12] = pdl::TP;
 }
 // returns a cudaError_t
 int pdl_k_launch(const pdl::Params* P, int n_ctas, int bwd, float* grad_params, float* grad_xi, double* stats, void* stream) {
@@ -830,7 +997,7 @@ void pdl_k_info(int* out) {
     out[0] = pdl::SM_TOTAL * 4; out[1] = pdl::NT; out[2] = pdl::ZSCR; out[3] = pdl::WPRIV; out[4] = pdl::CTA_OUT;
     out[5] = pdl::NPRM; out[6] = pdl::J; out[7] = pdl::K; out[8] = pdl::D; out[9] = pdl::NW;
     int np = 0; for (int t = 0; t < pdl::NPRM; ++t) np = pdl::prm_offset(t + 1); out[10] = np;
-    out[11] = PDL_MODE; out[12] = 8;
+    out[11] = PDL_MODE; out[12] = pdl::TP;
 }
 int pdl_k_launch(const pdl::Params* P, int n_ctas, int bwd, float* grad_params, float* grad_xi, double* stats, void* stream) {
     (void)stream;

@@ -125,6 +125,23 @@ uint64_t fnv1a(const std::string& s) {
 
 int smem_floats(const PlanMeta& m, int nw) {
     const int WP = m.wp, D = m.d, J = m.n_jets, H = m.hidden_layers, KX = std::max(m.n_rhs, 1);
+    if (m.engine == 1) {
+        const int JA = (J >= 3) ? 4 : J;
+        const int JB = (J <= 4) ? 0 : ((J == 5) ? 1 : ((J == 6) ? 2 : ((J <= 8) ? 4 : 8)));
+        const int SA = pad_stride(WP * JA), SB = JB ? pad_stride(WP * JB) : 0;
+        const int SD = 4 * m.gs, SF = WP, TP = 16;
+        const int NHH = H > 1 ? H - 1 : 0;
+        const int SO_XI = WP * D + WP + WP + 1 + 7 * H;
+        const int SACC = (SO_XI + KX * TP + 3) / 4 * 4;
+        const int SM_HH = (WP * D + WP + 3) / 4 * 4;
+        const int HH_B = m.dgrad_mma ? 4 * WP * SF : (2 * WP * SF + WP * SD);
+        const int HH_SIZE = (HH_B + WP + 3) / 4 * 4;
+        const int SM_WH = SM_HH + NHH * HH_SIZE;
+        const int SM_RAT = (SM_WH + WP + 1 + 3) / 4 * 4;
+        const int SM_SHARED = (SM_RAT + 8 * H + 2 * KX + 3) / 4 * 4;
+        const int BUF = std::max(8 * (SA + SB), 128);
+        return SM_SHARED + nw * (2 * BUF + SACC);
+    }
     const int NPL = WP / 4;
     const int JA = (J >= 3) ? 4 : J;
     const int JB = (J <= 4) ? 0 : ((J == 5) ? 1 : ((J == 6) ? 2 : ((J <= 8) ? 4 : 8)));
@@ -207,6 +224,15 @@ std::string generate_plan_source(const PlanSpec& spec, PlanMeta* meta_out) {
         meta.flops_per_point = f;
     }
     int nw = spec.warps_per_cta > 0 ? spec.warps_per_cta : 8;
+    // engine: the FP32-pipe kernel is the default.  The tensor-pipe kernel (PDL_ENGINE=mma) is 1.58x faster forward-only but
+    // not faster for forward+adjoint (measured, experiments/README.md); it keeps 2 x NPL x J activation values per lane in
+    // registers, so it only makes sense up to J = 4.
+    meta.engine = spec.engine >= 0 ? spec.engine : 0;
+    if (meta.engine == 1) {
+        meta.tile_points = 16;
+        meta.dgrad_mma = (spec.dgrad_mma == 0) ? 0 : 1;
+        if (smem_floats(meta, nw) * 4 > 227 * 1024) meta.dgrad_mma = 0;     // fall back to the FP32-pipe data gradient (one weight copy less)
+    }
     while (nw > 1 && smem_floats(meta, nw) * 4 > 227 * 1024) --nw;
     if (smem_floats(meta, nw) * 4 > 227 * 1024) throw std::runtime_error("plan does not fit in shared memory");
     meta.nw = nw;
@@ -220,7 +246,7 @@ std::string generate_plan_source(const PlanSpec& spec, PlanMeta* meta_out) {
     o << "#define PDL_D " << spec.d << "\n#define PDL_J " << J << "\n#define PDL_WP " << WP << "\n#define PDL_H " << H
       << "\n#define PDL_K " << K << "\n#define PDL_ACT " << spec.activation << "\n#define PDL_NS " << NS
       << "\n#define PDL_NW " << nw << "\n#define PDL_MODE " << spec.mode << "\n#define PDL_SF " << meta.sf
-      << "\n#define PDL_GS " << meta.gs << "\n";
+      << "\n#define PDL_GS " << meta.gs << "\n#define PDL_DGRAD_MMA " << meta.dgrad_mma << "\n";
     o << "#ifdef PDL_EMULATE\n#define PDL_GEN static inline\n#else\n#define PDL_GEN __host__ __device__ __forceinline__\n#endif\n";
 
     // widths / first-order component -> axis
@@ -358,7 +384,7 @@ std::string generate_plan_source(const PlanSpec& spec, PlanMeta* meta_out) {
         }
         o << "}\n";
     }
-    o << "#include \"jet_mlp_kernel.cuh\"\n";
+    o << (meta.engine == 1 ? "#include \"jet_mlp_kernel_mma.cuh\"\n" : "#include \"jet_mlp_kernel.cuh\"\n");
     if (meta_out) *meta_out = meta;
     return o.str();
 }

@@ -90,6 +90,10 @@ static int desc_to_spec(const pdl_plan_desc* d, pdl_host::PlanSpec* s) {
     }
     const char* nw = getenv("PDL_NW");
     if (nw && *nw) s->warps_per_cta = atoi(nw);
+    const char* dg = getenv("PDL_DGRAD_MMA");
+    if (dg && *dg) s->dgrad_mma = atoi(dg);
+    const char* eng = getenv("PDL_ENGINE");
+    if (eng && *eng) s->engine = (eng[0] == 'm' || eng[0] == 'M' || eng[0] == '1') ? 1 : 0;
     return 0;
 }
 
@@ -122,7 +126,8 @@ int pdl_plan_create(const pdl_plan_desc* desc, pdl_plan** out) {
         pdl_host::PlanMeta meta;
         const std::string src = pdl_host::generate_plan_source(spec, &meta);
         const std::string cdir = csrc_dir(), pdir = plans_dir();
-        const std::string hdr = read_file(cdir + "/jet_mlp_kernel.cuh") + read_file(cdir + "/kernel_params.h");
+        const std::string hdr = read_file(cdir + (meta.engine == 1 ? "/jet_mlp_kernel_mma.cuh" : "/jet_mlp_kernel.cuh")) +
+                                read_file(cdir + "/kernel_params.h");
         if (hdr.size() < 100) return fail("kernel template not found in " + cdir + " (set PDL_CSRC_DIR)");
         const char* xf = getenv("PDL_NVCC_FLAGS");
         const std::string flags = std::string("-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo ") + (xf ? xf : "");
@@ -220,7 +225,8 @@ int pdl_loss_launch(pdl_plan* p, const pdl_launch_args* a) {
     if (a->n_points > 0 && !a->points) return fail("points is null");
     int n_ctas = a->n_ctas;
     if (n_ctas <= 0) { int32_t sm = 0; if (pdl_device_sm_count(&sm)) return 1; n_ctas = sm; }
-    const long long tiles = (a->n_points + 7) / 8;
+    const int tp = p->kinfo[12] > 0 ? p->kinfo[12] : 8;
+    const long long tiles = (a->n_points + tp - 1) / tp;
     const long long need_ctas = (tiles + p->kinfo[9] - 1) / p->kinfo[9];
     if (need_ctas < n_ctas) n_ctas = (int)(need_ctas > 0 ? need_ctas : 1);
     const size_t need = pdl_plan_workspace_bytes(p, n_ctas);

@@ -94,3 +94,22 @@ def test_emulated_sharded_inv_n_is_additive():
     assert abs(a["loss"] + b["loss"] - whole["loss"]) <= 1e-6 * whole["loss"]
     assert rel_max(a["grad_params"] + b["grad_params"], whole["grad_params"]) <= 2e-6
     assert rel_max(a["grad_xi"] + b["grad_xi"], whole["grad_xi"]) <= 2e-6
+
+
+@pytest.mark.parametrize("name,dgrad", [("heat_tanh", "1"), ("heat_rational", "0"), ("kdv_tanh", "1"), ("wave_mixed_tanh", "0")])
+def test_emulated_tensor_pipe_engine(name, dgrad, monkeypatch):
+    """The opt-in mma.sync engine (jet_mlp_kernel_mma.cuh), with mma.sync.m16n8k8 modelled lane-exactly in the emulation."""
+    monkeypatch.setenv("PDL_ENGINE", "mma")
+    monkeypatch.setenv("PDL_DGRAD_MMA", dgrad)
+    g = GoldenCase(name)
+    desc, keep = desc_for(g)
+    assert "jet_mlp_kernel_mma.cuh" in L.plan_source(desc)
+    out = emu.run_emu(desc, g.points.numpy()[:37], [p.numpy() for p in g.params], g.xi.numpy(), np.array(g.mask, dtype=np.uint8), n_ctas=2)
+    net = g.net()
+    xi = g.xi.double().requires_grad_(True)
+    loss, resid, _ = O.coll_loss(lambda X: O.mlp_forward(net, X), xi, g.mask, g.points[:37].double(), g.lhs, g.rhs)
+    og = torch.autograd.grad(loss, net.tensors() + [xi])
+    assert abs(out["loss"] - float(loss.detach())) <= TOL * float(loss.detach())
+    assert rel_max(out["residual"], resid.detach().numpy()) <= TOL
+    assert rel_max(out["grad_params"], np.concatenate([x.numpy().ravel() for x in og[:-1]])) <= TOL
+    assert rel_max(out["grad_xi"], og[-1].numpy()) <= TOL

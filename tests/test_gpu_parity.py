@@ -408,3 +408,30 @@ def test_lbfgs_closure_reentry():
         last = P.Training([U], Xi, Mask, [coll], [X], [Y], derivs, lhs, rhs, 0.1, W, opt)
     assert np.isfinite(last["Total Losses"][0]) and last["Total Losses"][0] < first["Total Losses"][0]
     assert last["Residuals"][0].shape == (1024,)
+
+
+def test_tensor_pipe_engine_parity_subprocess():
+    """The opt-in mma.sync engine (PDL_ENGINE=mma) through the same public API, in a fresh process (plans are cached per process)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "import pde_learn_b200 as P\n"
+        "from tests.helpers import GoldenCase, rel_max\n"
+        "from tests.test_gpu_parity import _network_from_golden, _terms\n"
+        "for name in ('heat_tanh', 'heat_rational'):\n"
+        "    g = GoldenCase(name); U = _network_from_golden(g, P); derivs, lhs, rhs = _terms(P, g.lhs, g.rhs)\n"
+        "    xi = g.xi.to('cuda').requires_grad_(True)\n"
+        "    loss, r = P.Coll_Loss(U, xi, torch.tensor(g.mask), g.points.to('cuda'), derivs, lhs, rhs); loss.backward()\n"
+        "    got = np.concatenate([p.grad.cpu().numpy().ravel() for p in U.parameters()])\n"
+        "    ref = np.concatenate([x.numpy().ravel() for x in g.grads])\n"
+        "    assert abs(float(loss.detach()) - float(g.z['coll_loss'])) <= 1e-5 * float(g.z['coll_loss'])\n"
+        "    assert rel_max(r.cpu().numpy(), g.z['residual']) <= 1e-5 and rel_max(got, ref) <= 1e-5\n"
+        "    assert rel_max(xi.grad.cpu().numpy(), g.z['grad_xi']) <= 1e-5\n"
+        "    f = P.Evaluate_Derivatives(U, derivs, g.points.to('cuda')).cpu().numpy()\n"
+        "    assert all(rel_max(f[j], g.z['features'][j]) <= 1e-5 for j in range(len(derivs)))\n"
+        "print('MMA_ENGINE_OK')\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, PDL_ENGINE="mma")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "MMA_ENGINE_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])
