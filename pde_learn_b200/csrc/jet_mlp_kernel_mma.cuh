@@ -1,14 +1,12 @@
 // jet_mlp_kernel_mma.cuh -- fused jet-MLP + library-residual forward/adjoint kernel for sm_100a, tensor-pipe variant.
 //
-// Same contract, helpers and reductions as jet_mlp_kernel.cuh (see there for the reference map), but the two contractions
-// whose A operand is produced by the lane itself -- forward  z = W h  and data gradient  hb = zb W -- run as 3xTF32
-// mma.sync.m16n8k8 on the tensor pipe, concurrently with the FP32 pipe that keeps the jet activations, the weight gradient
-// and the epilogue.  A warp tile is 16 points (one m16 row block); lane = 4g + t owns points {g, g+8} and the neurons
-// {8j+2t, 8j+2t+1}: with the k index relabelled the same way, a lane's accumulator fragment of neuron tile j IS its A fragment
-// of k-step j, so activations never travel through shared memory between layers.  FP32-class accuracy comes from the split
-// x = hi + lo (hi = TF32 part): D += lo*Bhi + hi*Blo + hi*Bhi (measured 9e-7 relative, scripts/ubench/tc_gemm.cu).
+// Same contract, tiling (8 points per warp tile), scratch, reductions and helpers as jet_mlp_kernel.cuh (see there for the
+// reference map).  The contractions whose A operand is produced by the lane itself -- forward  z = W h  and, optionally, the
+// data gradient  hb = zb W  -- run as 3xTF32 mma.sync.m16n8k8 on the tensor pipe, concurrently with the FP32 pipe that keeps
+// the jet activations, the weight gradient and the epilogue.  FP32-class accuracy comes from the split x = hi + lo
+// (hi = TF32(x), lo = TF32(x - hi)):  D += lo*Bhi + hi*Blo + hi*Bhi.
 //
-// Included at the END of a generated plan translation unit when the plan compiler picks this engine (J <= 4).
+// Included at the END of a generated plan translation unit when the plan compiler picks this engine (PDL_ENGINE=mma).
 // The same source compiles as plain C++ with -DPDL_EMULATE (mma.sync is modelled lane-exactly): TEST INFRASTRUCTURE only.
 #pragma once
 #include <stdint.h>
@@ -41,25 +39,25 @@ namespace pdl {
 
 constexpr int D = PDL_D, J = PDL_J, WP = PDL_WP, H = PDL_H, K = PDL_K, NS = PDL_NS, NW = PDL_NW;
 constexpr int KX = (K > 0) ? K : 1;
-constexpr int TP = 16;                      // points per warp tile: one m16 MMA row block
-constexpr int NT8 = WP / 8;                 // 8-wide neuron tiles (MMA n-tiles and k-steps)
-constexpr int NPL = WP / 4;                 // neurons per lane: 2 per neuron tile
-constexpr int NPN = WP / 8;                 // neurons per lane group along n in the weight gradient
-constexpr bool DGRAD_MMA = (PDL_DGRAD_MMA != 0);   // data gradient on the tensor pipe too (needs two more weight copies)
+constexpr int NPL = WP / 4;                 // neurons per lane group (fwd / dgrad micro-tile rows)
+constexpr int NPN = WP / 8;                 // neurons per lane group along n in wgrad
 constexpr int JA = (J >= 3) ? 4 : J;        // plane A width (comps 0..3)
 constexpr int JB = (J <= 4) ? 0 : ((J == 5) ? 1 : ((J == 6) ? 2 : ((J <= 8) ? 4 : 8)));   // plane B width (comps 4..)
 constexpr int pad_stride(int n) { int m = (n + 3) / 4 * 4; while (((m / 4) & 1) == 0) m += 4; return m; }
 constexpr int SA = pad_stride(WP * JA);     // floats per point in plane A (odd number of 16B chunks)
 constexpr int SB = (JB > 0) ? pad_stride(WP * JB) : 0;
-constexpr int SF = WP;                      // row stride of the fragment-ordered weight copies (40: rows 8 banks apart)
-constexpr int GS = PDL_GS;                  // group stride of the FFMA dgrad weight copy  Wd[n][g4][i]
+constexpr int SF = WP;                      // row stride of the fragment-ordered weight copies (rows 8 banks apart for WP = 40)
+constexpr int NT8 = WP / 8;                 // 8-wide neuron tiles (MMA n-tiles and k-steps)
+constexpr int NM = (J + 1) / 2;             // component pairs = m16 row blocks per neuron tile
+constexpr bool DGRAD_MMA = (PDL_DGRAD_MMA != 0);   // data gradient on the tensor pipe too (two more weight copies)
+constexpr int GS = PDL_GS;                  // group stride of the dgrad weight copy  Wd[n][g4][i]
 constexpr int SD = 4 * GS;
 constexpr int NHH = (H > 1) ? (H - 1) : 0;  // hidden->hidden linear layers
 constexpr int NACC = NPN * NPL + NPN;       // wgrad accumulators per lane (weights + bias)
 constexpr int NACC4 = (NACC + 3) / 4 * 4;
 constexpr int WPRIV_LAYER = NACC4 * 32;     // floats per warp per hidden->hidden layer
 constexpr int WPRIV = NHH * WPRIV_LAYER;
-constexpr int ZS_LAYER = 2 * NPL * 32 * (JA + JB);
+constexpr int ZS_LAYER = NPL * 32 * (JA + JB);
 constexpr int ZSCR = NHH * ZS_LAYER;        // floats of pre-activation scratch per warp
 
 // small per-warp accumulators (shared memory), in floats
@@ -68,19 +66,17 @@ constexpr int SO_B0 = SO_W0 + WP * D;       // [WP]
 constexpr int SO_WH = SO_B0 + WP;           // [WP]
 constexpr int SO_BH = SO_WH + WP;           // [1]
 constexpr int SO_RAT = SO_BH + 1;           // [H][7]
-constexpr int SO_XI = SO_RAT + 7 * H;       // [KX][TP] one slot per point of the tile
-constexpr int SACC = (SO_XI + KX * TP + 3) / 4 * 4;
+constexpr int SO_XI = SO_RAT + 7 * H;       // [KX][8] one slot per point-lane
+constexpr int SACC = (SO_XI + KX * 8 + 3) / 4 * 4;
 constexpr int SACC_OUT = SO_XI + KX;        // what a CTA exports (xi slots summed)
 
 // shared-memory map (floats).  Shared part first, then NW private parts.
 constexpr int SM_W0 = 0;
 constexpr int SM_B0 = SM_W0 + WP * D;
-constexpr int SM_HH = (SM_B0 + WP + 3) / 4 * 4;
-// per hidden->hidden layer: W hi/lo [n][k] (forward B fragments), then either W^T hi/lo [k][n] (dgrad B fragments)
-// or the FFMA dgrad copy Wd[n][g4][i]; bias
-constexpr int HH_WHI = 0, HH_WLO = WP * SF;
-constexpr int HH_THI = 2 * WP * SF, HH_TLO = 3 * WP * SF;
-constexpr int HH_WD = 2 * WP * SF;
+constexpr int SM_HH = (SM_B0 + WP + 3) / 4 * 4;              // per hidden->hidden layer: Wf, Wd, bias
+// per hidden->hidden layer: W hi/lo [n][k] (forward B fragments), then either W^T hi/lo [k][n] (dgrad B fragments) or the
+// FP32-pipe dgrad copy Wd[n][t][i]; bias
+constexpr int HH_WHI = 0, HH_WLO = WP * SF, HH_THI = 2 * WP * SF, HH_TLO = 3 * WP * SF, HH_WD = 2 * WP * SF;
 constexpr int HH_B = DGRAD_MMA ? 4 * WP * SF : (2 * WP * SF + WP * SD);
 constexpr int HH_SIZE = (HH_B + WP + 3) / 4 * 4;
 constexpr int SM_WH = SM_HH + NHH * HH_SIZE;
@@ -89,7 +85,7 @@ constexpr int SM_RAT = (SM_BH + 1 + 3) / 4 * 4;              // [H][8]: a0..a3, 
 constexpr int SM_XI = SM_RAT + 8 * H;                        // xi with masked entries zeroed
 constexpr int SM_GM = SM_XI + KX;                            // 1 - mask
 constexpr int SM_SHARED = (SM_GM + KX + 3) / 4 * 4;
-constexpr int BUF = (8 * (SA + SB) > 128) ? 8 * (SA + SB) : 128;   // 8 points at a time; also hosts 64 doubles at warp exit
+constexpr int BUF = (8 * (SA + SB) > 128) ? 8 * (SA + SB) : 128;   // also hosts 64 doubles at warp exit
 constexpr int SM_WARP = 2 * BUF + SACC;                      // bufH, bufZ, small accumulators
 constexpr int SM_TOTAL = SM_SHARED + NW * SM_WARP;
 constexpr int NT = NW * 32;
@@ -152,7 +148,6 @@ template <int W> PDL_DEV void stgw(float* p, const float* v) {
     else if (W == 2) { pdl_f2 a; a.x = v[0]; a.y = v[1]; stg2(p, a); }
     else if (W == 1) stg1(p, v[0]);
 }
-constexpr int ZS_ROWS = 2 * NPL;            // scratch rows per layer: (point half, local neuron)
 constexpr int JT = JA + JB;                 // padded component count (>= J)
 // one (point, neuron) entry of a jet buffer: comps 0..JA-1 in plane A, the rest in plane B
 PDL_DEV void load_entry(const float* A, const float* B, float (&v)[J]) {
@@ -175,12 +170,12 @@ PDL_DEV void scratch_store(float* zs, int slot, int i, int lane, const float (&v
 #pragma unroll
     for (int c = 0; c < JT; ++c) t[c] = (c < J) ? v[c < J ? c : 0] : 0.f;
     stgw<JA>(zs + slot * ZS_LAYER + (i * 32 + lane) * JA, t);
-    if (JB > 0) stgw<JB>(zs + slot * ZS_LAYER + ZS_ROWS * 32 * JA + (i * 32 + lane) * JB, t + JA);
+    if (JB > 0) stgw<JB>(zs + slot * ZS_LAYER + NPL * 32 * JA + (i * 32 + lane) * JB, t + JA);
 }
 PDL_DEV void scratch_load(const float* zs, int slot, int i, int lane, float (&v)[J]) {
     float t[JT];
     ldgw<JA>(zs + slot * ZS_LAYER + (i * 32 + lane) * JA, t);
-    if (JB > 0) ldgw<JB>(zs + slot * ZS_LAYER + ZS_ROWS * 32 * JA + (i * 32 + lane) * JB, t + JA);
+    if (JB > 0) ldgw<JB>(zs + slot * ZS_LAYER + NPL * 32 * JA + (i * 32 + lane) * JB, t + JA);
 #pragma unroll
     for (int c = 0; c < J; ++c) v[c] = t[c];
 }
@@ -202,8 +197,10 @@ PDL_DEV void xor_add(float (&v)[PDL_NL][N], int m) {
 // warp-level tensor-core step: D(16x8) += A(16x8) * B(8x8), TF32 inputs, FP32 accumulate (mma.sync.m16n8k8)
 //   lane = 4*g + t:  A: a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);  B: b0 (k=t, n=g) b1 (k=t+4, n=g);
 //                    C: c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
-// Rows are the 16 points of the tile.  The k index is a summation index, so it is relabelled: slot t <-> neuron 8s+2t and
-// slot t+4 <-> neuron 8s+2t+1, which makes a lane's C fragment of neuron tile s exactly its A fragment of k-step s.
+// Rows 0-7 are jet component 2m of the tile's 8 points, rows 8-15 component 2m+1 of the SAME points (m = component pair), so a
+// lane (g, t) holds every component of point g for its neurons and the jet activation stays lane-local.  The k index is a
+// summation index, so it is relabelled: slot t <-> neuron 8s+2t and slot t+4 <-> neuron 8s+2t+1, which makes a lane's C
+// fragment of neuron tile s exactly its A fragment of k-step s: activations never pass through shared memory between layers.
 // ---------------------------------------------------------------------------------------------
 PDL_DEV uint32_t f2u(float x) {
 #ifdef PDL_EMULATE
@@ -374,14 +371,13 @@ PDL_DEV void stage_thread2(const Params& P, float* sm, int tid) {
             const float w = W[e];
             uint32_t uh, ul;
             split_tf32(w, uh, ul);
-            const float hi = u2f(uh), lo = u2f(ul);
-            base[HH_WHI + n * SF + k] = hi;
-            base[HH_WLO + n * SF + k] = lo;
+            base[HH_WHI + n * SF + k] = u2f(uh);
+            base[HH_WLO + n * SF + k] = u2f(ul);
             if (DGRAD_MMA) {
-                base[HH_THI + k * SF + n] = hi;
-                base[HH_TLO + k * SF + n] = lo;
+                base[HH_THI + k * SF + n] = u2f(uh);
+                base[HH_TLO + k * SF + n] = u2f(ul);
             } else {
-                // FFMA dgrad copy grouped by the lane column that owns input neuron k: t = (k%8)/2, i = 2*(k/8) + k%2
+                // FP32-pipe dgrad copy grouped by the lane column that owns input neuron k: t = (k%8)/2, i = 2*(k/8) + k%2
                 base[HH_WD + n * SD + ((k & 7) >> 1) * GS + 2 * (k >> 3) + (k & 1)] = w;
             }
         }
@@ -407,9 +403,6 @@ PDL_DEV void stage_thread2(const Params& P, float* sm, int tid) {
 // ---------------------------------------------------------------------------------------------
 // the per-warp tile loop
 // ---------------------------------------------------------------------------------------------
-// element of a fragment array belonging to (point half pp, local neuron i): tile i>>1, register 2*pp + (i&1)
-#define PDL_FR(arr, i, c, pp) arr[(i) >> 1][c][PDL_L][2 * (pp) + ((i) & 1)]
-
 template <bool BWD>
 PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, int n_warps
 #ifndef PDL_EMULATE
@@ -421,64 +414,66 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
     float* sacc = bufZ + BUF;
     float* zs = BWD ? (P.zscratch + (size_t)gwarp * ZSCR) : nullptr;
     float* wp = BWD ? (P.wpriv + (size_t)gwarp * WPRIV) : nullptr;
-    const long long n_tiles = (P.n_points + TP - 1) / TP;
+    const long long n_tiles = (P.n_points + 7) / 8;
     const float two_inv_n = (float)(2.0 * P.inv_n);
 
     double lsum[PDL_NL], asum[PDL_NL];
     PDL_FOR_LANES { lsum[PDL_L] = 0.0; asum[PDL_L] = 0.0; }
 
-    float x[PDL_NL][2][D];
-    float hf[NT8][J][PDL_NL][4];      // activation jets as C/A fragments: [neuron tile][component][lane][2*pp + e]
-    float hbf[NT8][J][PDL_NL][4];     // adjoint jets flowing backwards, same layout
-    float uu[PDL_NL][2 * J];
-    float ub[PDL_NL][2][J];
+    float x[PDL_NL][D];
+    float h[PDL_NL][NPL][J];          // activation jets of the lane's neurons (layer being produced)
+    float hb[PDL_NL][NPL][J];         // adjoint jets flowing backwards
+    float uu[PDL_NL][J];
+    float ub[PDL_NL][J];
+    float valid[PDL_NL];
     bool first = true;
 
     for (long long tile = gwarp; tile < n_tiles; tile += n_warps, first = false) {
-        // ---------------- layer 0 forward (CUDA cores: K = d is tiny) ----------------
+        // ---------------- layer 0 forward ----------------
         PDL_FOR_LANES {
-            const int g = lane >> 2, t = lane & 3;
+            const int pg = lane >> 2, g4 = lane & 3;
+            const long long p = tile * 8 + pg;
+            valid[PDL_L] = (p < P.n_points) ? 1.f : 0.f;
 #pragma unroll
-            for (int pp = 0; pp < 2; ++pp) {
-                const long long p = tile * TP + g + 8 * pp;
+            for (int dd = 0; dd < D; ++dd) x[PDL_L][dd] = (p < P.n_points) ? P.points[p * D + dd] : 0.f;
 #pragma unroll
-                for (int dd = 0; dd < D; ++dd) x[PDL_L][pp][dd] = (p < P.n_points) ? P.points[p * D + dd] : 0.f;
-#pragma unroll
-                for (int i = 0; i < NPL; ++i) {
-                    float z[J], hv[J];
-                    layer0_preact(sm, own_neuron(t, i), x[PDL_L][pp], z);
-                    act_forward(z, sm + SM_RAT, hv);
-#pragma unroll
-                    for (int c = 0; c < J; ++c) PDL_FR(hf, i, c, pp) = hv[c];
-                }
+            for (int i = 0; i < NPL; ++i) {
+                float z[J];
+                layer0_preact(sm, own_neuron(g4, i), x[PDL_L], z);
+                act_forward(z, sm + SM_RAT, h[PDL_L][i]);
             }
         }
-        // ---------------- hidden -> hidden layers, forward: 3xTF32 on the tensor pipe ----------------
+        // ---------------- hidden -> hidden layers, forward ----------------
         for (int l = 1; l < H; ++l) {
+            // 3xTF32 on the tensor pipe: accumulator fragments [neuron tile][component pair][lane][2*(c&1) + (i&1)]
             const float* Whi = sm + SM_HH + (l - 1) * HH_SIZE + HH_WHI;
             const float* Wlo = sm + SM_HH + (l - 1) * HH_SIZE + HH_WLO;
             const float* bl = sm + SM_HH + (l - 1) * HH_SIZE + HH_B;
-            float acc[NT8][J][PDL_NL][4];
+            float accf[NT8][NM][PDL_NL][4];
             PDL_FOR_LANES {
                 const int t = lane & 3;
 #pragma unroll
                 for (int q = 0; q < NT8; ++q) {
-                    const float b0 = bl[8 * q + 2 * t], b1 = bl[8 * q + 2 * t + 1];
-                    acc[q][0][PDL_L][0] = b0; acc[q][0][PDL_L][1] = b1; acc[q][0][PDL_L][2] = b0; acc[q][0][PDL_L][3] = b1;
 #pragma unroll
-                    for (int c = 1; c < J; ++c) { acc[q][c][PDL_L][0] = 0.f; acc[q][c][PDL_L][1] = 0.f; acc[q][c][PDL_L][2] = 0.f; acc[q][c][PDL_L][3] = 0.f; }
+                    for (int m = 0; m < NM; ++m) { accf[q][m][PDL_L][0] = 0.f; accf[q][m][PDL_L][1] = 0.f; accf[q][m][PDL_L][2] = 0.f; accf[q][m][PDL_L][3] = 0.f; }
+                    accf[q][0][PDL_L][0] = bl[8 * q + 2 * t];            // bias enters component 0 only
+                    accf[q][0][PDL_L][1] = bl[8 * q + 2 * t + 1];
                 }
             }
 #pragma unroll
             for (int s = 0; s < NT8; ++s) {
-                uint32_t ahi[J][PDL_NL][4], alo[J][PDL_NL][4];
+                uint32_t ahi[NM][PDL_NL][4], alo[NM][PDL_NL][4];
                 PDL_FOR_LANES {
 #pragma unroll
-                    for (int c = 0; c < J; ++c) {
-                        split_tf32(hf[s][c][PDL_L][0], ahi[c][PDL_L][0], alo[c][PDL_L][0]);
-                        split_tf32(hf[s][c][PDL_L][2], ahi[c][PDL_L][1], alo[c][PDL_L][1]);
-                        split_tf32(hf[s][c][PDL_L][1], ahi[c][PDL_L][2], alo[c][PDL_L][2]);
-                        split_tf32(hf[s][c][PDL_L][3], ahi[c][PDL_L][3], alo[c][PDL_L][3]);
+                    for (int m = 0; m < NM; ++m) {
+                        // a0 (comp 2m, neuron 8s+2t)  a1 (comp 2m+1, same neuron)  a2 (comp 2m, neuron 8s+2t+1)  a3 (comp 2m+1, ...)
+                        const float v0 = h[PDL_L][2 * s][2 * m], v2 = h[PDL_L][2 * s + 1][2 * m];
+                        const float v1 = (2 * m + 1 < J) ? h[PDL_L][2 * s][(2 * m + 1 < J) ? 2 * m + 1 : 0] : 0.f;
+                        const float v3 = (2 * m + 1 < J) ? h[PDL_L][2 * s + 1][(2 * m + 1 < J) ? 2 * m + 1 : 0] : 0.f;
+                        split_tf32(v0, ahi[m][PDL_L][0], alo[m][PDL_L][0]);
+                        split_tf32(v1, ahi[m][PDL_L][1], alo[m][PDL_L][1]);
+                        split_tf32(v2, ahi[m][PDL_L][2], alo[m][PDL_L][2]);
+                        split_tf32(v3, ahi[m][PDL_L][3], alo[m][PDL_L][3]);
                     }
                 }
 #pragma unroll
@@ -491,174 +486,154 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                         bhi[PDL_L][0] = f2u(vh.x); bhi[PDL_L][1] = f2u(vh.y); blo[PDL_L][0] = f2u(vl.x); blo[PDL_L][1] = f2u(vl.y);
                     }
 #pragma unroll
-                    for (int c = 0; c < J; ++c) {
-                        warp_mma(acc[q][c], alo[c], bhi);
-                        warp_mma(acc[q][c], ahi[c], blo);
-                        warp_mma(acc[q][c], ahi[c], bhi);
+                    for (int m = 0; m < NM; ++m) {
+                        warp_mma(accf[q][m], alo[m], bhi);
+                        warp_mma(accf[q][m], ahi[m], blo);
+                        warp_mma(accf[q][m], ahi[m], bhi);
                     }
                 }
             }
             PDL_FOR_LANES {
 #pragma unroll
-                for (int pp = 0; pp < 2; ++pp) {
+                for (int i = 0; i < NPL; ++i) {
+                    float z[J];
 #pragma unroll
-                    for (int i = 0; i < NPL; ++i) {
-                        float z[J], hv[J];
-#pragma unroll
-                        for (int c = 0; c < J; ++c) z[c] = PDL_FR(acc, i, c, pp);
-                        if (BWD) scratch_store(zs, l - 1, pp * NPL + i, lane, z);
-                        act_forward(z, sm + SM_RAT + l * 8, hv);
-#pragma unroll
-                        for (int c = 0; c < J; ++c) PDL_FR(hf, i, c, pp) = hv[c];
-                    }
+                    for (int c = 0; c < J; ++c) z[c] = accf[i >> 1][c >> 1][PDL_L][2 * (c & 1) + (i & 1)];
+                    if (BWD) scratch_store(zs, l - 1, i, lane, z);
+                    act_forward(z, sm + SM_RAT + l * 8, h[PDL_L][i]);
                 }
             }
         }
         // ---------------- output layer (identity activation) ----------------
         PDL_FOR_LANES {
-            const int t = lane & 3;
+            const int g4 = lane & 3;
 #pragma unroll
-            for (int q = 0; q < 2 * J; ++q) uu[PDL_L][q] = 0.f;
+            for (int c = 0; c < J; ++c) uu[PDL_L][c] = 0.f;
 #pragma unroll
             for (int i = 0; i < NPL; ++i) {
-                const float w = sm[SM_WH + own_neuron(t, i)];
+                const float w = sm[SM_WH + own_neuron(g4, i)];
 #pragma unroll
-                for (int pp = 0; pp < 2; ++pp) {
-#pragma unroll
-                    for (int c = 0; c < J; ++c) uu[PDL_L][pp * J + c] += w * PDL_FR(hf, i, c, pp);
-                }
+                for (int c = 0; c < J; ++c) uu[PDL_L][c] += w * h[PDL_L][i][c];
             }
         }
-        xor_add<2 * J>(uu, 1);
-        xor_add<2 * J>(uu, 2);
+        xor_add<J>(uu, 1);
+        xor_add<J>(uu, 2);
         // ---------------- library terms, residual, loss, seeds ----------------
         PDL_FOR_LANES {
-            const int g = lane >> 2, t = lane & 3;
+            const int pg = lane >> 2, g4 = lane & 3;
+            const long long p = tile * 8 + pg;
+            float u[J];
 #pragma unroll
-            for (int pp = 0; pp < 2; ++pp) {
-                const int pt = g + 8 * pp;
-                const long long p = tile * TP + pt;
-                const bool ok = p < P.n_points;
-                float u[J];
-#pragma unroll
-                for (int c = 0; c < J; ++c) u[c] = uu[PDL_L][pp * J + c];
-                u[0] += sm[SM_BH];
-                float r, du[J], T[KX];
-                pdl_epilogue(u, sm + SM_XI, r, du, T);
-                double rd = (double)r;
+            for (int c = 0; c < J; ++c) u[c] = uu[PDL_L][c];
+            u[0] += sm[SM_BH];
+            float r, du[J], T[KX];
+            pdl_epilogue(u, sm + SM_XI, r, du, T);
+            double rd = (double)r;
 #if PDL_MODE == 1
-                rd = ok ? ((double)r - P.targets[p]) : 0.0;      // f32 prediction - f64 target (Loss.py:56-59)
-                r = (float)rd;
+            rd = (p < P.n_points) ? ((double)r - P.targets[p]) : 0.0;      // f32 prediction - f64 target (Loss.py:56-59)
+            r = (float)rd;
 #endif
-                if (t == 0 && ok) {
-                    if (P.residual) P.residual[p] = r;
-                    if (P.features) {
+            const float v = valid[PDL_L];
+            if (g4 == 0 && v != 0.f) {
+                if (P.residual) P.residual[p] = r;
+                if (P.features) {
 #pragma unroll
-                        for (int c = 0; c < J; ++c) P.features[(size_t)c * P.n_points + p] = u[c];
-                    }
-                    lsum[PDL_L] += rd * rd;
-                    asum[PDL_L] += fabs(rd);
+                    for (int c = 0; c < J; ++c) P.features[(size_t)c * P.n_points + p] = u[c];
                 }
-                if (BWD) {
+                lsum[PDL_L] += rd * rd;
+                asum[PDL_L] += fabs(rd);
+            }
+            if (BWD) {
 #if PDL_MODE == 1
-                    const float rs = ok ? (float)(2.0 * P.inv_n * rd) : 0.f;
+                const float rs = (float)(2.0 * P.inv_n * rd) * v;
 #else
-                    const float rs = ok ? two_inv_n * r : 0.f;
+                const float rs = two_inv_n * r * v;
 #endif
 #pragma unroll
-                    for (int c = 0; c < J; ++c) ub[PDL_L][pp][c] = rs * du[c];
-                    if (t == 0) {
+                for (int c = 0; c < J; ++c) ub[PDL_L][c] = rs * du[c];
+                if (g4 == 0) {
 #pragma unroll
-                        for (int k = 0; k < K; ++k) sacc[SO_XI + k * TP + pt] -= rs * T[k] * sm[SM_GM + k];
-                    }
+                    for (int k = 0; k < K; ++k) sacc[SO_XI + k * 8 + pg] -= rs * T[k] * sm[SM_GM + k];
                 }
             }
         }
         if (!BWD) continue;
         // ---------------- output layer adjoint ----------------
         {
-            float gw[PDL_NL][NPL + 1];
+            float g[PDL_NL][NPL + 1];
             PDL_FOR_LANES {
-                const int t = lane & 3;
+                const int g4 = lane & 3;
 #pragma unroll
                 for (int i = 0; i < NPL; ++i) {
-                    const float w = sm[SM_WH + own_neuron(t, i)];
-                    float a = 0.f;
+                    float t = 0.f;
 #pragma unroll
-                    for (int pp = 0; pp < 2; ++pp) {
+                    for (int c = 0; c < J; ++c) t += ub[PDL_L][c] * h[PDL_L][i][c];
+                    g[PDL_L][i] = t;
+                    const float w = sm[SM_WH + own_neuron(g4, i)];
 #pragma unroll
-                        for (int c = 0; c < J; ++c) {
-                            a += ub[PDL_L][pp][c] * PDL_FR(hf, i, c, pp);
-                            PDL_FR(hbf, i, c, pp) = w * ub[PDL_L][pp][c];
-                        }
-                    }
-                    gw[PDL_L][i] = a;
+                    for (int c = 0; c < J; ++c) hb[PDL_L][i][c] = w * ub[PDL_L][c];
                 }
-                gw[PDL_L][NPL] = ub[PDL_L][0][0] + ub[PDL_L][1][0];
+                g[PDL_L][NPL] = ub[PDL_L][0];
             }
-            xor_add<NPL + 1>(gw, 4); xor_add<NPL + 1>(gw, 8); xor_add<NPL + 1>(gw, 16);
+            xor_add<NPL + 1>(g, 4); xor_add<NPL + 1>(g, 8); xor_add<NPL + 1>(g, 16);
             PDL_FOR_LANES {
-                const int g = lane >> 2, t = lane & 3;
-                if (g == 0) {
+                const int pg = lane >> 2, g4 = lane & 3;
+                if (pg == 0) {
 #pragma unroll
-                    for (int i = 0; i < NPL; ++i) sacc[SO_WH + own_neuron(t, i)] += gw[PDL_L][i];
-                    if (t == 0) sacc[SO_BH] += gw[PDL_L][NPL];
+                    for (int i = 0; i < NPL; ++i) sacc[SO_WH + own_neuron(g4, i)] += g[PDL_L][i];
+                    if (g4 == 0) sacc[SO_BH] += g[PDL_L][NPL];
                 }
             }
         }
         // ---------------- hidden -> hidden layers, adjoint ----------------
         for (int l = H - 1; l >= 1; --l) {
-            float zbf[NT8][J][PDL_NL][4];             // adjoint of the pre-activations, kept as A fragments for the dgrad MMAs
-            float wacc[PDL_NL][NACC4];                // weight-gradient register tile (NPN x NPL + bias), v1 lane mapping
             float ga[PDL_NL][7];
-            float* wpl = wp + (l - 1) * WPRIV_LAYER;
+            float zbk[PDL_NL][NPL][J];            // adjoint of the pre-activations kept for the tensor-pipe data gradient
             PDL_FOR_LANES {
+                const int pg = lane >> 2, g4 = lane & 3;
 #pragma unroll
                 for (int q = 0; q < 7; ++q) ga[PDL_L][q] = 0.f;
-                if (first) {
 #pragma unroll
-                    for (int a = 0; a < NACC4; ++a) wacc[PDL_L][a] = 0.f;
-                } else {
+                for (int i = 0; i < NPL; ++i) {
+                    const int n = own_neuron(g4, i);
+                    float z[J], zb[J];
+                    scratch_load(zs, l - 1, i, lane, z);
+                    act_adjoint(z, hb[PDL_L][i], sm + SM_RAT + l * 8, zb, ga[PDL_L]);
+                    store_entry(bufZ + pg * SA + n * JA, bufZ + 8 * SA + pg * SB + n * JB, zb);
+                    if (DGRAD_MMA) {
 #pragma unroll
-                    for (int a = 0; a < NACC4; a += 4) {
-                        const pdl_f4 v = ldg4(wpl + (a / 4 * 32 + lane) * 4);
-                        wacc[PDL_L][a] = v.x; wacc[PDL_L][a + 1] = v.y; wacc[PDL_L][a + 2] = v.z; wacc[PDL_L][a + 3] = v.w;
+                        for (int c = 0; c < J; ++c) zbk[PDL_L][i][c] = zb[c];
                     }
+                    // activations of the layer below (input of this linear layer), recomputed
+                    float zi[J], hi[J];
+                    if (l >= 2) scratch_load(zs, l - 2, i, lane, zi);
+                    else layer0_preact(sm, n, x[PDL_L], zi);
+                    act_forward(zi, sm + SM_RAT + (l - 1) * 8, hi);
+                    store_entry(bufH + pg * SA + n * JA, bufH + 8 * SA + pg * SB + n * JB, hi);
                 }
             }
-#pragma unroll 1
-            for (int pp = 0; pp < 2; ++pp) {
-                PDL_FOR_LANES {
-                    const int g = lane >> 2, t = lane & 3;
+            PDL_SYNCWARP();
+#if PDL_ACT == 1
+            xor_add<7>(ga, 1); xor_add<7>(ga, 2); xor_add<7>(ga, 4); xor_add<7>(ga, 8); xor_add<7>(ga, 16);
+            PDL_FOR_LANES { if (lane == 0) { for (int q = 0; q < 7; ++q) sacc[SO_RAT + l * 7 + q] += ga[PDL_L][q]; } }
+#endif
+            const float* Wd = sm + SM_HH + (l - 1) * HH_SIZE + HH_WD;
+            PDL_FOR_LANES {
+                const int pg = lane >> 2, g4 = lane & 3, g8 = lane >> 2;
+                // ---- weight gradient: Wbar[n][k] += sum_p sum_c zb[p][n][c] * h[p][k][c]   (n in g8 group, k in g4 group)
+                {
+                    float acc[NACC4];
+                    float* wpl = wp + (l - 1) * WPRIV_LAYER;
+                    if (first) {
 #pragma unroll
-                    for (int i = 0; i < NPL; ++i) {
-                        const int n = own_neuron(t, i);
-                        float z[J], zb[J], hbv[J];
-                        scratch_load(zs, l - 1, pp * NPL + i, lane, z);
+                        for (int a = 0; a < NACC4; ++a) acc[a] = 0.f;
+                    } else {
 #pragma unroll
-                        for (int c = 0; c < J; ++c) hbv[c] = (pp == 0) ? PDL_FR(hbf, i, c, 0) : PDL_FR(hbf, i, c, 1);
-                        act_adjoint(z, hbv, sm + SM_RAT + l * 8, zb, ga[PDL_L]);
-#pragma unroll
-                        for (int c = 0; c < J; ++c) { if (pp == 0) PDL_FR(zbf, i, c, 0) = zb[c]; else PDL_FR(zbf, i, c, 1) = zb[c]; }
-                        store_entry(bufZ + g * SA + n * JA, bufZ + 8 * SA + g * SB + n * JB, zb);
-                        // activations of the layer below (input of this linear layer), recomputed
-                        float zi[J], hi[J];
-                        if (l >= 2) scratch_load(zs, l - 2, pp * NPL + i, lane, zi);
-                        else {
-                            float xp[D];
-#pragma unroll
-                            for (int dd = 0; dd < D; ++dd) xp[dd] = (pp == 0) ? x[PDL_L][0][dd] : x[PDL_L][1][dd];
-                            layer0_preact(sm, n, xp, zi);
+                        for (int a = 0; a < NACC4; a += 4) {
+                            const pdl_f4 t = ldg4(wpl + (a / 4 * 32 + lane) * 4);
+                            acc[a] = t.x; acc[a + 1] = t.y; acc[a + 2] = t.z; acc[a + 3] = t.w;
                         }
-                        act_forward(zi, sm + SM_RAT + (l - 1) * 8, hi);
-                        store_entry(bufH + g * SA + n * JA, bufH + 8 * SA + g * SB + n * JB, hi);
                     }
-                }
-                PDL_SYNCWARP();
-                const float* Wd = sm + SM_HH + (l - 1) * HH_SIZE + HH_WD;
-                PDL_FOR_LANES {
-                    const int g = lane >> 2, g4 = lane & 3, g8 = lane >> 2;
-                    // ---- weight gradient over the 8 points in the buffers (FP32 pipe): Wbar[n][k] += sum_c zb[p][n][c] h[p][k][c]
 #pragma unroll 2
                     for (int q = 0; q < 8; ++q) {
                         float zq[NPN][J], hq[NPL][J];
@@ -671,81 +646,73 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
 #pragma unroll
                             for (int b = 0; b < NPL; ++b) {
 #pragma unroll
-                                for (int c = 0; c < J; ++c) wacc[PDL_L][a * NPL + b] += zq[a][c] * hq[b][c];
+                                for (int c = 0; c < J; ++c) acc[a * NPL + b] += zq[a][c] * hq[b][c];
                             }
-                            wacc[PDL_L][NPN * NPL + a] += zq[a][0];
+                            acc[NPN * NPL + a] += zq[a][0];
                         }
                     }
-                    if (!DGRAD_MMA) {
-                        // ---- data gradient on the FP32 pipe for this half: hb[p][k] = sum_n zb[p][n] W[n][k], k = own_neuron(t, i)
-                        float hacc[NPL][J];
 #pragma unroll
-                        for (int i = 0; i < NPL; ++i) {
+                    for (int a = 0; a < NACC4; a += 4) {
+                        pdl_f4 t; t.x = acc[a]; t.y = acc[a + 1]; t.z = acc[a + 2]; t.w = acc[a + 3];
+                        stg4(wpl + (a / 4 * 32 + lane) * 4, t);
+                    }
+                }
+                // ---- data gradient on the FP32 pipe: hb[p][k] = sum_n zb[p][n] * W[n][k]   (k = the lane's own neurons)
+                if (!DGRAD_MMA) {
 #pragma unroll
-                            for (int c = 0; c < J; ++c) hacc[i][c] = 0.f;
-                        }
-                        const float* zA = bufZ + g * SA;
-                        const float* zB = bufZ + 8 * SA + g * SB;
+                for (int i = 0; i < NPL; ++i) {
+#pragma unroll
+                    for (int c = 0; c < J; ++c) hb[PDL_L][i][c] = 0.f;
+                }
+                const float* zA = bufZ + pg * SA;
+                const float* zB = bufZ + 8 * SA + pg * SB;
 #pragma unroll 2
-                        for (int nc = 0; nc < WP; nc += 4) {
-                            float a[4][J];
+                for (int nc = 0; nc < WP; nc += 4) {
+                    float a[4][J];
 #pragma unroll
-                            for (int nn = 0; nn < 4; ++nn) load_entry(zA + (nc + nn) * JA, zB + (nc + nn) * JB, a[nn]);
+                    for (int nn = 0; nn < 4; ++nn) load_entry(zA + (nc + nn) * JA, zB + (nc + nn) * JB, a[nn]);
 #pragma unroll
-                            for (int nn = 0; nn < 4; ++nn) {
-                                const float* wr = Wd + (nc + nn) * SD + g4 * GS;
-                                float w[NPL];
+                    for (int nn = 0; nn < 4; ++nn) {
+                        const float* wr = Wd + (nc + nn) * SD + g4 * GS;
+                        float w[NPL];
 #pragma unroll
-                                for (int i = 0; i + 3 < NPL; i += 4) { const pdl_f4 v = ld4(wr + i); w[i] = v.x; w[i + 1] = v.y; w[i + 2] = v.z; w[i + 3] = v.w; }
-                                if ((NPL & 3) >= 2) { const pdl_f2 v = ld2(wr + (NPL & ~3)); w[(NPL & ~3)] = v.x; w[(NPL & ~3) + 1 < NPL ? (NPL & ~3) + 1 : 0] = v.y; }
-#pragma unroll
-                                for (int i = 0; i < NPL; ++i) {
-#pragma unroll
-                                    for (int c = 0; c < J; ++c) hacc[i][c] += a[nn][c] * w[i];
-                                }
-                            }
-                        }
+                        for (int i = 0; i + 3 < NPL; i += 4) { const pdl_f4 t = ld4(wr + i); w[i] = t.x; w[i + 1] = t.y; w[i + 2] = t.z; w[i + 3] = t.w; }
+                        if ((NPL & 3) >= 2) { const pdl_f2 t = ld2(wr + (NPL & ~3)); w[(NPL & ~3)] = t.x; w[(NPL & ~3) + 1 < NPL ? (NPL & ~3) + 1 : 0] = t.y; }
+                        if (NPL & 1) w[NPL - 1] = wr[NPL - 1];
 #pragma unroll
                         for (int i = 0; i < NPL; ++i) {
 #pragma unroll
-                            for (int c = 0; c < J; ++c) { if (pp == 0) PDL_FR(hbf, i, c, 0) = hacc[i][c]; else PDL_FR(hbf, i, c, 1) = hacc[i][c]; }
+                            for (int c = 0; c < J; ++c) hb[PDL_L][i][c] += a[nn][c] * w[i];
                         }
                     }
                 }
-                PDL_SYNCWARP();
-            }
-            PDL_FOR_LANES {
-#pragma unroll
-                for (int a = 0; a < NACC4; a += 4) {
-                    pdl_f4 v; v.x = wacc[PDL_L][a]; v.y = wacc[PDL_L][a + 1]; v.z = wacc[PDL_L][a + 2]; v.w = wacc[PDL_L][a + 3];
-                    stg4(wpl + (a / 4 * 32 + lane) * 4, v);
                 }
             }
-#if PDL_ACT == 1
-            xor_add<7>(ga, 1); xor_add<7>(ga, 2); xor_add<7>(ga, 4); xor_add<7>(ga, 8); xor_add<7>(ga, 16);
-            PDL_FOR_LANES { if (lane == 0) { for (int q = 0; q < 7; ++q) sacc[SO_RAT + l * 7 + q] += ga[PDL_L][q]; } }
-#endif
             if (DGRAD_MMA) {
-                // ---- data gradient on the tensor pipe: hb = zb W, A fragments straight from the registers
+                // ---- data gradient on the tensor pipe: hb = zb W, A fragments straight from the registers, B = W^T hi/lo
                 const float* Thi = sm + SM_HH + (l - 1) * HH_SIZE + HH_THI;
                 const float* Tlo = sm + SM_HH + (l - 1) * HH_SIZE + HH_TLO;
+                float hbfr[NT8][NM][PDL_NL][4];
                 PDL_FOR_LANES {
 #pragma unroll
                     for (int q = 0; q < NT8; ++q) {
 #pragma unroll
-                        for (int c = 0; c < J; ++c) { hbf[q][c][PDL_L][0] = 0.f; hbf[q][c][PDL_L][1] = 0.f; hbf[q][c][PDL_L][2] = 0.f; hbf[q][c][PDL_L][3] = 0.f; }
+                        for (int m = 0; m < NM; ++m) { hbfr[q][m][PDL_L][0] = 0.f; hbfr[q][m][PDL_L][1] = 0.f; hbfr[q][m][PDL_L][2] = 0.f; hbfr[q][m][PDL_L][3] = 0.f; }
                     }
                 }
 #pragma unroll
                 for (int s = 0; s < NT8; ++s) {
-                    uint32_t ahi[J][PDL_NL][4], alo[J][PDL_NL][4];
+                    uint32_t ahi[NM][PDL_NL][4], alo[NM][PDL_NL][4];
                     PDL_FOR_LANES {
 #pragma unroll
-                        for (int c = 0; c < J; ++c) {
-                            split_tf32(zbf[s][c][PDL_L][0], ahi[c][PDL_L][0], alo[c][PDL_L][0]);
-                            split_tf32(zbf[s][c][PDL_L][2], ahi[c][PDL_L][1], alo[c][PDL_L][1]);
-                            split_tf32(zbf[s][c][PDL_L][1], ahi[c][PDL_L][2], alo[c][PDL_L][2]);
-                            split_tf32(zbf[s][c][PDL_L][3], ahi[c][PDL_L][3], alo[c][PDL_L][3]);
+                        for (int m = 0; m < NM; ++m) {
+                            const float v0 = zbk[PDL_L][2 * s][2 * m], v2 = zbk[PDL_L][2 * s + 1][2 * m];
+                            const float v1 = (2 * m + 1 < J) ? zbk[PDL_L][2 * s][(2 * m + 1 < J) ? 2 * m + 1 : 0] : 0.f;
+                            const float v3 = (2 * m + 1 < J) ? zbk[PDL_L][2 * s + 1][(2 * m + 1 < J) ? 2 * m + 1 : 0] : 0.f;
+                            split_tf32(v0, ahi[m][PDL_L][0], alo[m][PDL_L][0]);
+                            split_tf32(v1, ahi[m][PDL_L][1], alo[m][PDL_L][1]);
+                            split_tf32(v2, ahi[m][PDL_L][2], alo[m][PDL_L][2]);
+                            split_tf32(v3, ahi[m][PDL_L][3], alo[m][PDL_L][3]);
                         }
                     }
 #pragma unroll
@@ -758,43 +725,45 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                             bhi[PDL_L][0] = f2u(vh.x); bhi[PDL_L][1] = f2u(vh.y); blo[PDL_L][0] = f2u(vl.x); blo[PDL_L][1] = f2u(vl.y);
                         }
 #pragma unroll
-                        for (int c = 0; c < J; ++c) {
-                            warp_mma(hbf[q][c], alo[c], bhi);
-                            warp_mma(hbf[q][c], ahi[c], blo);
-                            warp_mma(hbf[q][c], ahi[c], bhi);
+                        for (int m = 0; m < NM; ++m) {
+                            warp_mma(hbfr[q][m], alo[m], bhi);
+                            warp_mma(hbfr[q][m], ahi[m], blo);
+                            warp_mma(hbfr[q][m], ahi[m], bhi);
                         }
                     }
                 }
+                PDL_FOR_LANES {
+#pragma unroll
+                    for (int i = 0; i < NPL; ++i) {
+#pragma unroll
+                        for (int c = 0; c < J; ++c) hb[PDL_L][i][c] = hbfr[i >> 1][c >> 1][PDL_L][2 * (c & 1) + (i & 1)];
+                    }
+                }
             }
+            PDL_SYNCWARP();
         }
         // ---------------- layer 0 adjoint ----------------
         {
             float g0[PDL_NL][NPL * (D + 1)];
             float ga[PDL_NL][7];
             PDL_FOR_LANES {
-                const int t = lane & 3;
+                const int g4 = lane & 3;
 #pragma unroll
                 for (int q = 0; q < 7; ++q) ga[PDL_L][q] = 0.f;
 #pragma unroll
-                for (int q = 0; q < NPL * (D + 1); ++q) g0[PDL_L][q] = 0.f;
+                for (int i = 0; i < NPL; ++i) {
+                    const int n = own_neuron(g4, i);
+                    float z[J], zb[J];
+                    layer0_preact(sm, n, x[PDL_L], z);
+                    act_adjoint(z, hb[PDL_L][i], sm + SM_RAT, zb, ga[PDL_L]);
 #pragma unroll
-                for (int pp = 0; pp < 2; ++pp) {
+                    for (int dd = 0; dd < D; ++dd) {
+                        float t = zb[0] * x[PDL_L][dd];
 #pragma unroll
-                    for (int i = 0; i < NPL; ++i) {
-                        float z[J], zb[J], hbv[J];
-                        layer0_preact(sm, own_neuron(t, i), x[PDL_L][pp], z);
-#pragma unroll
-                        for (int c = 0; c < J; ++c) hbv[c] = PDL_FR(hbf, i, c, pp);
-                        act_adjoint(z, hbv, sm + SM_RAT, zb, ga[PDL_L]);
-#pragma unroll
-                        for (int dd = 0; dd < D; ++dd) {
-                            float a = zb[0] * x[PDL_L][pp][dd];
-#pragma unroll
-                            for (int c = 1; c < J; ++c) if (pdl_comp_axis(c) == dd) a += zb[c];
-                            g0[PDL_L][i * (D + 1) + dd] += a;
-                        }
-                        g0[PDL_L][i * (D + 1) + D] += zb[0];
+                        for (int c = 1; c < J; ++c) if (pdl_comp_axis(c) == dd) t += zb[c];
+                        g0[PDL_L][i * (D + 1) + dd] = t;
                     }
+                    g0[PDL_L][i * (D + 1) + D] = zb[0];
                 }
             }
             xor_add<NPL*(D + 1)>(g0, 4); xor_add<NPL*(D + 1)>(g0, 8); xor_add<NPL*(D + 1)>(g0, 16);
@@ -802,11 +771,11 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
             xor_add<7>(ga, 1); xor_add<7>(ga, 2); xor_add<7>(ga, 4); xor_add<7>(ga, 8); xor_add<7>(ga, 16);
 #endif
             PDL_FOR_LANES {
-                const int g = lane >> 2, t = lane & 3;
-                if (g == 0) {
+                const int pg = lane >> 2, g4 = lane & 3;
+                if (pg == 0) {
 #pragma unroll
                     for (int i = 0; i < NPL; ++i) {
-                        const int n = own_neuron(t, i);
+                        const int n = own_neuron(g4, i);
 #pragma unroll
                         for (int dd = 0; dd < D; ++dd) sacc[SO_W0 + n * D + dd] += g0[PDL_L][i * (D + 1) + dd];
                         sacc[SO_B0 + n] += g0[PDL_L][i * (D + 1) + D];
@@ -820,7 +789,7 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
         PDL_SYNCWARP();
     }
 
-    // ---- warp epilogue: a warp that never ran a tile must still publish zeros ----
+    // ---- warp epilogue: a warp that never ran a tile must still publish zeros; loss partials via shuffles ----
     if (BWD && first) {
         PDL_FOR_LANES {
             pdl_f4 zero; zero.x = zero.y = zero.z = zero.w = 0.f;
@@ -852,7 +821,7 @@ PDL_DEV void cta_tail_thread(const Params& P, const float* sm, int cta, int tid,
             for (int w = 0; w < NW; ++w) {
                 const float* sacc = sm + SM_SHARED + w * SM_WARP + 2 * BUF;
                 if (e < SO_XI) s += sacc[e];
-                else { const int k = e - SO_XI; for (int q = 0; q < TP; ++q) s += sacc[SO_XI + k * TP + q]; }
+                else { const int k = e - SO_XI; for (int q = 0; q < 8; ++q) s += sacc[SO_XI + k * 8 + q]; }
             }
             out[WPRIV + e] = s;
         }
@@ -961,7 +930,7 @@ void pdl_k_info(int* out) {
     out[0] = pdl::SM_TOTAL * 4; out[1] = pdl::NT; out[2] = pdl::ZSCR; out[3] = pdl::WPRIV; out[4] = pdl::CTA_OUT;
     out[5] = pdl::NPRM; out[6] = pdl::J; out[7] = pdl::K; out[8] = pdl::D; out[9] = pdl::NW;
     int np = 0; for (int t = 0; t < pdl::NPRM; ++t) np = pdl::prm_offset(t + 1); out[10] = np;
-    out[11] = PDL_MODE; out[12] = pdl::TP;
+    out[11] = PDL_MODE; out[12] = 8;
 }
 // returns a cudaError_t
 int pdl_k_launch(const pdl::Params* P, int n_ctas, int bwd, float* grad_params, float* grad_xi, double* stats, void* stream) {
@@ -997,7 +966,7 @@ void pdl_k_info(int* out) {
     out[0] = pdl::SM_TOTAL * 4; out[1] = pdl::NT; out[2] = pdl::ZSCR; out[3] = pdl::WPRIV; out[4] = pdl::CTA_OUT;
     out[5] = pdl::NPRM; out[6] = pdl::J; out[7] = pdl::K; out[8] = pdl::D; out[9] = pdl::NW;
     int np = 0; for (int t = 0; t < pdl::NPRM; ++t) np = pdl::prm_offset(t + 1); out[10] = np;
-    out[11] = PDL_MODE; out[12] = pdl::TP;
+    out[11] = PDL_MODE; out[12] = 8;
 }
 int pdl_k_launch(const pdl::Params* P, int n_ctas, int bwd, float* grad_params, float* grad_xi, double* stats, void* stream) {
     (void)stream;

@@ -129,7 +129,7 @@ int smem_floats(const PlanMeta& m, int nw) {
         const int JA = (J >= 3) ? 4 : J;
         const int JB = (J <= 4) ? 0 : ((J == 5) ? 1 : ((J == 6) ? 2 : ((J <= 8) ? 4 : 8)));
         const int SA = pad_stride(WP * JA), SB = JB ? pad_stride(WP * JB) : 0;
-        const int SD = 4 * m.gs, SF = WP, TP = 16;
+        const int SD = 4 * m.gs, SF = WP, TP = 8;
         const int NHH = H > 1 ? H - 1 : 0;
         const int SO_XI = WP * D + WP + WP + 1 + 7 * H;
         const int SACC = (SO_XI + KX * TP + 3) / 4 * 4;
@@ -224,13 +224,13 @@ std::string generate_plan_source(const PlanSpec& spec, PlanMeta* meta_out) {
         meta.flops_per_point = f;
     }
     int nw = spec.warps_per_cta > 0 ? spec.warps_per_cta : 8;
-    // engine: the FP32-pipe kernel is the default.  The tensor-pipe kernel (PDL_ENGINE=mma) is 1.58x faster forward-only but
-    // not faster for forward+adjoint (measured, experiments/README.md); it keeps 2 x NPL x J activation values per lane in
-    // registers, so it only makes sense up to J = 4.
-    meta.engine = spec.engine >= 0 ? spec.engine : 0;
+    // engine: the tensor-pipe kernel (forward and, when the extra weight copies fit, data gradient as 3xTF32 mma.sync) is
+    // 1.07-1.18x faster than the FP32-pipe kernel for forward+adjoint and 1.5x forward-only (measured, experiments/README.md);
+    // it needs a hidden->hidden layer to have anything to contract.  PDL_ENGINE=ffma|mma overrides.
+    meta.engine = spec.engine >= 0 ? spec.engine : ((H >= 2) ? 1 : 0);
     if (meta.engine == 1) {
-        meta.tile_points = 16;
-        meta.dgrad_mma = (spec.dgrad_mma == 0) ? 0 : 1;
+        meta.tile_points = 8;
+        meta.dgrad_mma = (spec.dgrad_mma == 0) ? 0 : ((spec.dgrad_mma == 1 || WP <= 48) ? 1 : 0);   // wide nets would spill
         if (smem_floats(meta, nw) * 4 > 227 * 1024) meta.dgrad_mma = 0;     // fall back to the FP32-pipe data gradient (one weight copy less)
     }
     while (nw > 1 && smem_floats(meta, nw) * 4 > 227 * 1024) --nw;

@@ -96,14 +96,17 @@ def test_emulated_sharded_inv_n_is_additive():
     assert rel_max(a["grad_xi"] + b["grad_xi"], whole["grad_xi"]) <= 2e-6
 
 
-@pytest.mark.parametrize("name,dgrad", [("heat_tanh", "1"), ("heat_rational", "0"), ("kdv_tanh", "1"), ("wave_mixed_tanh", "0")])
-def test_emulated_tensor_pipe_engine(name, dgrad, monkeypatch):
-    """The opt-in mma.sync engine (jet_mlp_kernel_mma.cuh), with mma.sync.m16n8k8 modelled lane-exactly in the emulation."""
-    monkeypatch.setenv("PDL_ENGINE", "mma")
+@pytest.mark.parametrize("name,engine,dgrad", [("heat_tanh", "mma", "1"), ("heat_rational", "mma", "0"), ("kdv_tanh", "mma", "1"),
+                                               ("wave_mixed_tanh", "mma", "0"), ("heat_tanh", "ffma", "0"), ("ks_rational", "ffma", "0"),
+                                               ("rd2d_tanh", "ffma", "0"), ("burgers_rational20", "ffma", "0")])
+def test_emulated_engines_explicitly(name, engine, dgrad, monkeypatch):
+    """Both kernel families by explicit choice: the tensor-pipe engine (jet_mlp_kernel_mma.cuh, mma.sync.m16n8k8 modelled
+    lane-exactly, with and without the tensor-pipe data gradient) and the FP32-pipe engine (jet_mlp_kernel.cuh)."""
+    monkeypatch.setenv("PDL_ENGINE", engine)
     monkeypatch.setenv("PDL_DGRAD_MMA", dgrad)
     g = GoldenCase(name)
     desc, keep = desc_for(g)
-    assert "jet_mlp_kernel_mma.cuh" in L.plan_source(desc)
+    assert ("jet_mlp_kernel_mma.cuh" in L.plan_source(desc)) == (engine == "mma")
     out = emu.run_emu(desc, g.points.numpy()[:37], [p.numpy() for p in g.params], g.xi.numpy(), np.array(g.mask, dtype=np.uint8), n_ctas=2)
     net = g.net()
     xi = g.xi.double().requires_grad_(True)

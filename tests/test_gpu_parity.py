@@ -410,8 +410,9 @@ def test_lbfgs_closure_reentry():
     assert last["Residuals"][0].shape == (1024,)
 
 
-def test_tensor_pipe_engine_parity_subprocess():
-    """The opt-in mma.sync engine (PDL_ENGINE=mma) through the same public API, in a fresh process (plans are cached per process)."""
+def test_fp32_pipe_engine_parity_subprocess():
+    """The FP32-pipe kernel family (PDL_ENGINE=ffma; the default is the tensor-pipe engine) through the same public API, in a
+    fresh process (plans are cached per process)."""
     import subprocess
     import sys
     code = (
@@ -420,7 +421,7 @@ def test_tensor_pipe_engine_parity_subprocess():
         "import pde_learn_b200 as P\n"
         "from tests.helpers import GoldenCase, rel_max\n"
         "from tests.test_gpu_parity import _network_from_golden, _terms\n"
-        "for name in ('heat_tanh', 'heat_rational'):\n"
+        "for name in ('heat_tanh', 'ks_rational'):\n"
         "    g = GoldenCase(name); U = _network_from_golden(g, P); derivs, lhs, rhs = _terms(P, g.lhs, g.rhs)\n"
         "    xi = g.xi.to('cuda').requires_grad_(True)\n"
         "    loss, r = P.Coll_Loss(U, xi, torch.tensor(g.mask), g.points.to('cuda'), derivs, lhs, rhs); loss.backward()\n"
@@ -431,7 +432,7 @@ def test_tensor_pipe_engine_parity_subprocess():
         "    assert rel_max(xi.grad.cpu().numpy(), g.z['grad_xi']) <= 1e-5\n"
         "    f = P.Evaluate_Derivatives(U, derivs, g.points.to('cuda')).cpu().numpy()\n"
         "    assert all(rel_max(f[j], g.z['features'][j]) <= 1e-5 for j in range(len(derivs)))\n"
-        "print('MMA_ENGINE_OK')\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    env = dict(os.environ, PDL_ENGINE="mma")
+        "print('ENGINE_OK')\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, PDL_ENGINE="ffma")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
-    assert r.returncode == 0 and "MMA_ENGINE_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])
+    assert r.returncode == 0 and "ENGINE_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])
