@@ -3,7 +3,7 @@
 // Same contract, tiling (8 points per warp tile), scratch, reductions and helpers as jet_mlp_kernel.cuh (see there for the
 // reference map).  The contractions whose A operand is produced by the lane itself -- forward  z = W h  and, optionally, the
 // data gradient  hb = zb W  -- run as 3xTF32 mma.sync.m16n8k8 on the tensor pipe, concurrently with the FP32 pipe that keeps
-// the jet activations, the weight gradient and the epilogue.  FP32-class accuracy comes from the split x = hi + lo
+// the jet activations and the epilogue (and the weight gradient unless PDL_WGRAD_MMA moves it to the tensor pipe as well).  FP32-class accuracy comes from the split x = hi + lo
 // (hi = TF32(x), lo = TF32(x - hi)):  D += lo*Bhi + hi*Blo + hi*Bhi.
 //
 // Included at the END of a generated plan translation unit when the plan compiler picks this engine (PDL_ENGINE=mma).
@@ -50,12 +50,22 @@ constexpr int SF = WP;                      // row stride of the fragment-ordere
 constexpr int NT8 = WP / 8;                 // 8-wide neuron tiles (MMA n-tiles and k-steps)
 constexpr int NM = (J + 1) / 2;             // component pairs = m16 row blocks per neuron tile
 constexpr bool DGRAD_MMA = (PDL_DGRAD_MMA != 0);   // data gradient on the tensor pipe too (two more weight copies)
+constexpr bool WGRAD_MMA = (PDL_WGRAD_MMA != 0);   // weight gradient on the tensor pipe (k = the tile's 8 points, one k-step per component)
+constexpr int NMT = (WP + 15) / 16;         // m16 tiles over the output neurons of a weight-gradient block
+constexpr int NFRAG = NMT * NT8;            // C fragments of one layer's weight gradient
+#ifndef PDL_WGRAD_NTB
+#define PDL_WGRAD_NTB 3
+#endif
+#ifndef PDL_WGRAD_ROLL_MT
+#define PDL_WGRAD_ROLL_MT (PDL_J >= 5)      // measured: from J = 5 on the unrolled m-tile loop costs more in instruction fetch than it gains
+#endif
+constexpr int NTB = PDL_WGRAD_NTB;          // n8 tiles per weight-gradient step (independent MMA chains vs registers)
 constexpr int GS = PDL_GS;                  // group stride of the dgrad weight copy  Wd[n][g4][i]
 constexpr int SD = 4 * GS;
 constexpr int NHH = (H > 1) ? (H - 1) : 0;  // hidden->hidden linear layers
 constexpr int NACC = NPN * NPL + NPN;       // wgrad accumulators per lane (weights + bias)
 constexpr int NACC4 = (NACC + 3) / 4 * 4;
-constexpr int WPRIV_LAYER = NACC4 * 32;     // floats per warp per hidden->hidden layer
+constexpr int WPRIV_LAYER = WGRAD_MMA ? (NFRAG + 1) * 128 : NACC4 * 32;   // floats per warp per hidden->hidden layer (MMA: C fragments + bias slot)
 constexpr int WPRIV = NHH * WPRIV_LAYER;
 constexpr int ZS_LAYER = NPL * 32 * (JA + JB);
 constexpr int ZSCR = NHH * ZS_LAYER;        // floats of pre-activation scratch per warp
@@ -216,20 +226,32 @@ PDL_DEV float u2f(uint32_t u) {
     return __uint_as_float(u);
 #endif
 }
-// round-to-nearest (ties away) conversion FP32 -> TF32 bit pattern (low 13 mantissa bits zero)
-PDL_DEV uint32_t tf32_rna(float x) {
-#ifdef PDL_EMULATE
-    return (f2u(x) + 0x1000u) & 0xFFFFE000u;
-#else
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-#endif
-}
+// round-to-nearest (ties away) FP32 -> TF32 bit pattern (low 13 mantissa bits zero).  Written as integer arithmetic on purpose:
+// cvt.rna.tf32.f32 expands to four SASS instructions (FSETP/IADD3/LOP3/SEL, the NaN path), this is two and identical for every
+// finite input (inf stays inf; a NaN still ends up as a NaN in the accumulator through the lo part).
+PDL_DEV uint32_t tf32_rna(float x) { return (f2u(x) + 0x1000u) & 0xFFFFE000u; }
 // FP32 value -> (hi, lo): hi = TF32(x), lo = TF32(x - hi); x - hi is exact in FP32, so hi + lo carries ~22 mantissa bits
 PDL_DEV void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
     hi = tf32_rna(x);
+#ifdef PDL_SPLIT_RAW_ALL
+    lo = f2u(x - u2f(hi));
+#else
     lo = tf32_rna(x - u2f(hi));
+#endif
+}
+// same without rounding the low part: the tensor pipe reads only the upper 19 bits of an operand register, i.e. it truncates lo
+// itself (error < 2^-21 |x|, the size of the dropped lo*lo term).  Used where splits dominate the instruction count and the
+// result is a long sum in which the truncation errors average out (weight gradient).
+PDL_DEV void split_tf32_raw(float x, uint32_t& hi, uint32_t& lo) {
+    hi = tf32_rna(x);
+    lo = f2u(x - u2f(hi));
+}
+PDL_DEV void split_tf32_dg(float x, uint32_t& hi, uint32_t& lo) {
+#ifdef PDL_SPLIT_ROUND_DG
+    split_tf32(x, hi, lo);
+#else
+    split_tf32_raw(x, hi, lo);
+#endif
 }
 PDL_DEV void warp_mma(float (&d)[PDL_NL][4], const uint32_t (&a)[PDL_NL][4], const uint32_t (&b)[PDL_NL][2]) {
 #ifdef PDL_EMULATE
@@ -369,8 +391,7 @@ PDL_DEV void stage_thread2(const Params& P, float* sm, int tid) {
         for (int e = tid; e < wout * win; e += NT) {
             const int n = e / win, k = e - n * win;
             const float w = W[e];
-            uint32_t uh, ul;
-            split_tf32(w, uh, ul);
+            const uint32_t uh = tf32_rna(w), ul = tf32_rna(w - u2f(uh));   // staged once per CTA: round the low part too
             base[HH_WHI + n * SF + k] = u2f(uh);
             base[HH_WLO + n * SF + k] = u2f(ul);
             if (DGRAD_MMA) {
@@ -621,7 +642,7 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
             PDL_FOR_LANES {
                 const int pg = lane >> 2, g4 = lane & 3, g8 = lane >> 2;
                 // ---- weight gradient: Wbar[n][k] += sum_p sum_c zb[p][n][c] * h[p][k][c]   (n in g8 group, k in g4 group)
-                {
+                if (!WGRAD_MMA) {
                     float acc[NACC4];
                     float* wpl = wp + (l - 1) * WPRIV_LAYER;
                     if (first) {
@@ -688,6 +709,105 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                 }
                 }
             }
+            if (WGRAD_MMA) {
+                // ---- weight gradient on the tensor pipe.  Wbar[n][k] = sum_c sum_p zb[p][n][c] h[p][k][c]: M = n (m16 tiles), N = k
+                // (n8 tiles), one k8-step per jet component with the tile's 8 points as the summation index (slot t <-> point 2t,
+                // slot t+4 <-> point 2t+1: conflict-free 16-byte reads of the [point][neuron][comp] buffers).  Each C fragment is
+                // accumulated from zero on the tensor pipe (which truncates) and added to the running FP32 partial sum with a
+                // rounded FADD, so the long sum over tiles keeps round-to-nearest behaviour.
+                float* wpl = wp + (l - 1) * WPRIV_LAYER;
+                float bsel[PDL_NL][2];
+                PDL_FOR_LANES { bsel[PDL_L][0] = 0.f; bsel[PDL_L][1] = 0.f; }
+#if PDL_WGRAD_ROLL_MT
+#pragma unroll 1
+#else
+#pragma unroll
+#endif
+                for (int mt = 0; mt < NMT; ++mt) {
+                    uint32_t ahi[J][PDL_NL][4], alo[J][PDL_NL][4];
+                    float bs[PDL_NL][2];
+                    PDL_FOR_LANES {
+                        const int g = lane >> 2, t = lane & 3;
+                        const int n0 = 16 * mt + g, n1 = n0 + 8;
+                        float v[4][J];
+                        load_entry(bufZ + (2 * t) * SA + n0 * JA, bufZ + 8 * SA + (2 * t) * SB + n0 * JB, v[0]);
+                        load_entry(bufZ + (2 * t + 1) * SA + n0 * JA, bufZ + 8 * SA + (2 * t + 1) * SB + n0 * JB, v[2]);
+                        if (16 * mt + 8 < WP) {
+                            load_entry(bufZ + (2 * t) * SA + n1 * JA, bufZ + 8 * SA + (2 * t) * SB + n1 * JB, v[1]);
+                            load_entry(bufZ + (2 * t + 1) * SA + n1 * JA, bufZ + 8 * SA + (2 * t + 1) * SB + n1 * JB, v[3]);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < J; ++c) { v[1][c] = 0.f; v[3][c] = 0.f; }
+                        }
+#pragma unroll
+                        for (int c = 0; c < J; ++c) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) split_tf32_raw(v[q][c], ahi[c][PDL_L][q], alo[c][PDL_L][q]);
+                        }
+                        bs[PDL_L][0] = v[0][0] + v[2][0];                 // bias gradient: sum over points of component 0
+                        bs[PDL_L][1] = v[1][0] + v[3][0];
+                    }
+                    xor_add<2>(bs, 1); xor_add<2>(bs, 2);
+                    PDL_FOR_LANES { if ((lane & 3) == mt) { bsel[PDL_L][0] = bs[PDL_L][0]; bsel[PDL_L][1] = bs[PDL_L][1]; } }
+#pragma unroll
+                    for (int nt0 = 0; nt0 < NT8; nt0 += NTB) {
+                        // NTB n8 tiles at a time, three accumulators each (lo*hi, hi*lo, hi*hi): 3*NTB independent MMA chains of length J
+                        uint32_t bhi[NTB][J][PDL_NL][2], blo[NTB][J][PDL_NL][2];
+                        float c4[NTB][3][PDL_NL][4];
+                        PDL_FOR_LANES {
+                            const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+                            for (int b = 0; b < NTB; ++b) {
+                                if (nt0 + b < NT8) {
+                                    const int k = 8 * (nt0 + b) + g;
+                                    float w0[J], w1[J];
+                                    load_entry(bufH + (2 * t) * SA + k * JA, bufH + 8 * SA + (2 * t) * SB + k * JB, w0);
+                                    load_entry(bufH + (2 * t + 1) * SA + k * JA, bufH + 8 * SA + (2 * t + 1) * SB + k * JB, w1);
+#pragma unroll
+                                    for (int c = 0; c < J; ++c) {
+                                        split_tf32_raw(w0[c], bhi[b][c][PDL_L][0], blo[b][c][PDL_L][0]);
+                                        split_tf32_raw(w1[c], bhi[b][c][PDL_L][1], blo[b][c][PDL_L][1]);
+                                    }
+                                }
+#pragma unroll
+                                for (int q = 0; q < 3; ++q) { c4[b][q][PDL_L][0] = 0.f; c4[b][q][PDL_L][1] = 0.f; c4[b][q][PDL_L][2] = 0.f; c4[b][q][PDL_L][3] = 0.f; }
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < J; ++c) {
+#pragma unroll
+                            for (int b = 0; b < NTB; ++b) {
+                                if (nt0 + b < NT8) {
+                                    warp_mma(c4[b][0], alo[c], bhi[b][c]);
+                                    warp_mma(c4[b][1], ahi[c], blo[b][c]);
+                                    warp_mma(c4[b][2], ahi[c], bhi[b][c]);
+                                }
+                            }
+                        }
+                        PDL_FOR_LANES {
+#pragma unroll
+                            for (int b = 0; b < NTB; ++b) {
+                                if (nt0 + b < NT8) {
+                                    float* q = wpl + ((mt * NT8 + nt0 + b) * 32 + lane) * 4;
+                                    pdl_f4 r;
+                                    r.x = (c4[b][0][PDL_L][0] + c4[b][1][PDL_L][0]) + c4[b][2][PDL_L][0];
+                                    r.y = (c4[b][0][PDL_L][1] + c4[b][1][PDL_L][1]) + c4[b][2][PDL_L][1];
+                                    r.z = (c4[b][0][PDL_L][2] + c4[b][1][PDL_L][2]) + c4[b][2][PDL_L][2];
+                                    r.w = (c4[b][0][PDL_L][3] + c4[b][1][PDL_L][3]) + c4[b][2][PDL_L][3];
+                                    if (!first) { const pdl_f4 o = ldg4(q); r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
+                                    stg4(q, r);
+                                }
+                            }
+                        }
+                    }
+                }
+                PDL_FOR_LANES {                                            // bias slot: lane (g, t) owns neurons 16t+g and 16t+g+8
+                    float* q = wpl + (NFRAG * 32 + lane) * 4;
+                    pdl_f4 r; r.x = bsel[PDL_L][0]; r.y = bsel[PDL_L][1]; r.z = 0.f; r.w = 0.f;
+                    if (!first) { const pdl_f4 o = ldg4(q); r.x += o.x; r.y += o.y; }
+                    stg4(q, r);
+                }
+            }
             if (DGRAD_MMA) {
                 // ---- data gradient on the tensor pipe: hb = zb W, A fragments straight from the registers, B = W^T hi/lo
                 const float* Thi = sm + SM_HH + (l - 1) * HH_SIZE + HH_THI;
@@ -709,10 +829,10 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                             const float v0 = zbk[PDL_L][2 * s][2 * m], v2 = zbk[PDL_L][2 * s + 1][2 * m];
                             const float v1 = (2 * m + 1 < J) ? zbk[PDL_L][2 * s][(2 * m + 1 < J) ? 2 * m + 1 : 0] : 0.f;
                             const float v3 = (2 * m + 1 < J) ? zbk[PDL_L][2 * s + 1][(2 * m + 1 < J) ? 2 * m + 1 : 0] : 0.f;
-                            split_tf32(v0, ahi[m][PDL_L][0], alo[m][PDL_L][0]);
-                            split_tf32(v1, ahi[m][PDL_L][1], alo[m][PDL_L][1]);
-                            split_tf32(v2, ahi[m][PDL_L][2], alo[m][PDL_L][2]);
-                            split_tf32(v3, ahi[m][PDL_L][3], alo[m][PDL_L][3]);
+                            split_tf32_dg(v0, ahi[m][PDL_L][0], alo[m][PDL_L][0]);
+                            split_tf32_dg(v1, ahi[m][PDL_L][1], alo[m][PDL_L][1]);
+                            split_tf32_dg(v2, ahi[m][PDL_L][2], alo[m][PDL_L][2]);
+                            split_tf32_dg(v3, ahi[m][PDL_L][3], alo[m][PDL_L][3]);
                         }
                     }
 #pragma unroll
@@ -869,6 +989,18 @@ PDL_DEV void reduce_item(const ReduceArgs& R, int e) {
         const int a = (q / 128) * 4 + (q & 3), lane = (q >> 2) & 31;
         const int g8 = lane >> 2, g4 = lane & 3;
         const int win = pdl_width(l), wout = pdl_width(l + 1);
+        if (WGRAD_MMA) {                                     // C-fragment order: [m16 tile][n8 tile][lane][4], then the bias slot
+            const int frag = q / 128, i = q & 3;
+            if (frag < NFRAG) {
+                const int mt = frag / NT8, nt = frag % NT8;
+                const int n = 16 * mt + g8 + ((i & 2) ? 8 : 0), k = 8 * nt + 2 * g4 + (i & 1);
+                if (n < wout && k < win) R.grad_params[prm_offset(2 * l) + n * win + k] = v;
+            } else if (i < 2) {
+                const int n = 16 * g4 + g8 + 8 * i;
+                if (g4 < NMT && n < wout) R.grad_params[prm_offset(2 * l + 1) + n] = v;
+            }
+            return;
+        }
         if (a < NPN * NPL) {
             const int n = g8 * NPN + a / NPL, k = g4 * NPL + a % NPL;
             if (n < wout && k < win) R.grad_params[prm_offset(2 * l) + n * win + k] = v;

@@ -232,6 +232,9 @@ std::string generate_plan_source(const PlanSpec& spec, PlanMeta* meta_out) {
         meta.tile_points = 8;
         meta.dgrad_mma = (spec.dgrad_mma == 0) ? 0 : ((spec.dgrad_mma == 1 || WP <= 48) ? 1 : 0);   // wide nets would spill
         if (smem_floats(meta, nw) * 4 > 227 * 1024) meta.dgrad_mma = 0;     // fall back to the FP32-pipe data gradient (one weight copy less)
+        // weight gradient on the tensor pipe: measured faster everywhere except Rational nets that also run the data gradient there
+        // (register pressure; heat 5.44 -> 5.81 ms, burgers 7.08 -> 7.74 ms), see experiments/README.md
+        meta.wgrad_mma = (spec.wgrad_mma >= 0) ? (spec.wgrad_mma ? 1 : 0) : ((spec.activation == 1 && meta.dgrad_mma) ? 0 : 1);
     }
     while (nw > 1 && smem_floats(meta, nw) * 4 > 227 * 1024) --nw;
     if (smem_floats(meta, nw) * 4 > 227 * 1024) throw std::runtime_error("plan does not fit in shared memory");
@@ -246,7 +249,8 @@ std::string generate_plan_source(const PlanSpec& spec, PlanMeta* meta_out) {
     o << "#define PDL_D " << spec.d << "\n#define PDL_J " << J << "\n#define PDL_WP " << WP << "\n#define PDL_H " << H
       << "\n#define PDL_K " << K << "\n#define PDL_ACT " << spec.activation << "\n#define PDL_NS " << NS
       << "\n#define PDL_NW " << nw << "\n#define PDL_MODE " << spec.mode << "\n#define PDL_SF " << meta.sf
-      << "\n#define PDL_GS " << meta.gs << "\n#define PDL_DGRAD_MMA " << meta.dgrad_mma << "\n";
+      << "\n#define PDL_GS " << meta.gs << "\n#define PDL_DGRAD_MMA " << meta.dgrad_mma
+      << "\n#define PDL_WGRAD_MMA " << meta.wgrad_mma << "\n";
     o << "#ifdef PDL_EMULATE\n#define PDL_GEN static inline\n#else\n#define PDL_GEN __host__ __device__ __forceinline__\n#endif\n";
 
     // widths / first-order component -> axis

@@ -92,6 +92,8 @@ static int desc_to_spec(const pdl_plan_desc* d, pdl_host::PlanSpec* s) {
     if (nw && *nw) s->warps_per_cta = atoi(nw);
     const char* dg = getenv("PDL_DGRAD_MMA");
     if (dg && *dg) s->dgrad_mma = atoi(dg);
+    const char* wg = getenv("PDL_WGRAD_MMA");
+    if (wg && *wg) s->wgrad_mma = atoi(wg);
     const char* eng = getenv("PDL_ENGINE");
     if (eng && *eng) s->engine = (eng[0] == 'm' || eng[0] == 'M' || eng[0] == '1') ? 1 : 0;
     return 0;

@@ -29,8 +29,11 @@ def probe(w, act, B, bwd=True, reps=8):
     gp = torch.empty(plan.n_param_scalars, dtype=torch.float32, device=dev)
     gx = torch.empty(K, dtype=torch.float32, device=dev)
     ts = []
+    flush = torch.empty(768 << 20, dtype=torch.uint8, device=dev) if os.environ.get("PDL_PROBE_FLUSH") else None
     for i in range(reps + 3):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if flush is not None:
+            flush.zero_()
         a.record()
         plan.launch(pts, prm, xi, mask, None, 1.0 / B, bwd, resid, None, gp if bwd else None, gx if bwd else None, stats)
         b.record()

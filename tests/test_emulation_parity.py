@@ -96,17 +96,21 @@ def test_emulated_sharded_inv_n_is_additive():
     assert rel_max(a["grad_xi"] + b["grad_xi"], whole["grad_xi"]) <= 2e-6
 
 
-@pytest.mark.parametrize("name,engine,dgrad", [("heat_tanh", "mma", "1"), ("heat_rational", "mma", "0"), ("kdv_tanh", "mma", "1"),
-                                               ("wave_mixed_tanh", "mma", "0"), ("heat_tanh", "ffma", "0"), ("ks_rational", "ffma", "0"),
-                                               ("rd2d_tanh", "ffma", "0"), ("burgers_rational20", "ffma", "0")])
-def test_emulated_engines_explicitly(name, engine, dgrad, monkeypatch):
+@pytest.mark.parametrize("name,engine,dgrad,wgrad", [
+    ("heat_tanh", "mma", "1", "0"), ("heat_rational", "mma", "0", "0"), ("kdv_tanh", "mma", "1", "0"), ("wave_mixed_tanh", "mma", "0", "0"),
+    ("heat_tanh", "mma", "1", "1"), ("heat_rational", "mma", "0", "1"), ("kdv_tanh", "mma", "1", "1"), ("ks_tanh", "mma", "0", "1"),
+    ("burgers_rational20", "mma", "1", "1"), ("heat3d_tanh", "mma", "0", "1"), ("rd2d_tanh", "mma", "0", "1"),
+    ("heat_tanh", "ffma", "0", "0"), ("ks_rational", "ffma", "0", "0"), ("rd2d_tanh", "ffma", "0", "0"), ("burgers_rational20", "ffma", "0", "0")])
+def test_emulated_engines_explicitly(name, engine, dgrad, wgrad, monkeypatch):
     """Both kernel families by explicit choice: the tensor-pipe engine (jet_mlp_kernel_mma.cuh, mma.sync.m16n8k8 modelled
-    lane-exactly, with and without the tensor-pipe data gradient) and the FP32-pipe engine (jet_mlp_kernel.cuh)."""
+    lane-exactly, with and without the tensor-pipe data gradient / weight gradient) and the FP32-pipe engine (jet_mlp_kernel.cuh)."""
     monkeypatch.setenv("PDL_ENGINE", engine)
     monkeypatch.setenv("PDL_DGRAD_MMA", dgrad)
+    monkeypatch.setenv("PDL_WGRAD_MMA", wgrad)
     g = GoldenCase(name)
     desc, keep = desc_for(g)
     assert ("jet_mlp_kernel_mma.cuh" in L.plan_source(desc)) == (engine == "mma")
+    assert ("#define PDL_WGRAD_MMA 1" in L.plan_source(desc)) == (engine == "mma" and wgrad == "1")
     out = emu.run_emu(desc, g.points.numpy()[:37], [p.numpy() for p in g.params], g.xi.numpy(), np.array(g.mask, dtype=np.uint8), n_ctas=2)
     net = g.net()
     xi = g.xi.double().requires_grad_(True)
