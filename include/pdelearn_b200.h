@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PDL_ABI_VERSION 1
+#define PDL_ABI_VERSION 2
 
 #define PDL_ACT_TANH 0      /* torch.nn.Tanh            (Code/Classes/Network.py:161-162) */
 #define PDL_ACT_RATIONAL 1  /* Rational (3,2), trainable (Code/Classes/Network.py:7-59)   */
@@ -84,6 +84,10 @@ typedef struct {
     size_t workspace_bytes;
     int32_t n_ctas;             /* 0 = one persistent CTA per SM of the current device                    */
     void* stream;               /* cudaStream_t                                                           */
+    const int64_t* n_points_dev;/* optional, device int64[1] (ABI 2): the row count is read on the device at kernel start
+                                   (clamped to n_points, which becomes the capacity used for grid and workspace sizing) and
+                                   the mean uses 1/rows instead of inv_n.  Lets one captured CUDA graph serve epochs whose
+                                   number of targeted collocation points differs (Code/main.py:290-297,365-384).        */
 } pdl_launch_args;
 
 const char* pdl_last_error(void);
@@ -120,6 +124,11 @@ int pdl_l2_squared_loss(const float* const* params, const int32_t* sizes, int32_
 int pdl_sample_points(const double* bounds, int32_t d, int64_t n, uint64_t seed, uint64_t first_index, float* out,
                       void* stream);
 
+/* Same sampler with the Philox key read from device memory at kernel start, so that a captured CUDA graph draws
+ * fresh points on every replay (the caller advances *seed_dev between replays).  seed_dev: device uint64[1]. */
+int pdl_sample_points_dev(const double* bounds, int32_t d, int64_t n, const uint64_t* seed_dev, uint64_t first_index,
+                          float* out, void* stream);
+
 /* Targeted collocation points (Code/main.py:365-384): sum and sum of squares of |r| over the first
  * n_random rows (stats: device double[2]) and compaction of rows with |r| >= cutoff (order preserved).
  * out_count: device int64[1]; out_points must hold n rows; block_scratch: device int32[(n+1023)/1024 + 1]. */
@@ -132,10 +141,23 @@ int pdl_select_targeted(const float* points, const float* residual, int64_t n, i
 int pdl_targeted_update(const float* points, const float* residual, int64_t n, int64_t n_random, int32_t d,
                         float* out_points, int64_t* out_count, double* stats, int32_t* block_scratch, void* stream);
 
+/* Same with the row count on the device (n_dev: device int64[1], clamped to `capacity`) and a bounded output:
+ * at most out_capacity rows are written and *out_count = min(selected, out_capacity).  For captured epochs. */
+int pdl_targeted_update_dev(const float* points, const float* residual, int64_t capacity, const int64_t* n_dev,
+                            int64_t n_random, int32_t d, float* out_points, int64_t out_capacity, int64_t* out_count,
+                            double* stats, int32_t* block_scratch, void* stream);
+
 /* Fused Adam update over a flat parameter vector (torch.optim.Adam semantics, no weight decay / amsgrad):
  * the optimiser step of Code/Test_Train.py:193 for the Adam branch of Code/main.py:232-246. */
 int pdl_adam_step(float* theta, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
                   double beta1, double beta2, double eps, int64_t step, void* stream);
+
+/* The same update for a table of up to 48 tensors in one launch, with the step count read from device memory
+ * (step_dev: device float[1], the value torch.optim.Adam keeps in state["step"]; the caller increments it before the
+ * call).  theta/grad/exp_avg/exp_avg_sq/sizes: HOST arrays of n_tensors entries (device pointers / element counts). */
+int pdl_adam_step_multi(float* const* theta, const float* const* grad, float* const* exp_avg, float* const* exp_avg_sq,
+                        const int64_t* sizes, int32_t n_tensors, double lr, double beta1, double beta2, double eps,
+                        const float* step_dev, void* stream);
 
 /* out[i] = wa*a[i] + wb*b[i] + wc*c[i] (b, c may be NULL): the weighted sum wC*dColl + wD*dData + wL2*dL2 of one
  * closure (Code/Test_Train.py:167-170) in a single pass over the flat gradient vectors. */

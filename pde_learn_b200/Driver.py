@@ -62,12 +62,15 @@ def Run_Epochs(U_List: List[Network], Xi: torch.Tensor, Mask: torch.Tensor, Inpu
                p: float, Weights: Dict[str, float], Optimizer: torch.optim.Optimizer, Num_Epochs: int,
                Num_Train_Coll_Points: int, Num_Test_Coll_Points: int = 0, Test_Inputs_List=None, Test_Targets_List=None,
                Point_Sampler: Optional[Callable] = None, Process_Group=None, Seed: int = 0,
-               On_Epoch: Optional[Callable] = None) -> Dict:
+               On_Epoch: Optional[Callable] = None, Use_CUDA_Graph: bool = False, Max_Targeted: Optional[int] = None) -> Dict:
     """
     The epoch loop of Code/main.py:281-405: per epoch and per data set sample Num_Train_Coll_Points random points,
     append last epoch's targeted points, run Training, optionally Testing on fresh points, update the targeted points.
     `Point_Sampler(data_set_index, epoch, n)` may supply the random points (default: on-device Philox sampler).
     Returns the loss histories (numpy arrays, one row per epoch).
+    `Use_CUDA_Graph=True` (Adam, one process, default sampler) replays the whole epoch as one captured CUDA graph
+    (Epoch_Graph.Captured_Epochs): same numbers, no per-epoch host work; epochs are replayed in chunks of 10 unless Testing
+    is requested every epoch.
     """
     S = len(U_List)
     dev = Xi.device
@@ -78,6 +81,32 @@ def Run_Epochs(U_List: List[Network], Xi: torch.Tensor, Mask: torch.Tensor, Inpu
             "Test Coll": numpy.zeros((Num_Epochs, S)), "Test Data": numpy.zeros((Num_Epochs, S)),
             "Num Targeted": numpy.zeros((Num_Epochs, S), dtype=numpy.int64)}
     sample = Point_Sampler or (lambda i, e, n: Generate_Points(Bounds_List[i], n, dev, Seed=(Seed * 1000003 + e) * 64 + i))
+    if Use_CUDA_Graph:
+        if Point_Sampler is not None or Process_Group is not None:
+            raise ValueError("Use_CUDA_Graph works with the built-in sampler in one process")
+        from .Epoch_Graph import Captured_Epochs
+        cap = Captured_Epochs(U_List, Xi, Mask, Inputs_List, Targets_List, Bounds_List, Derivatives, LHS_Term, RHS_Terms, p, Weights,
+                              Optimizer, Num_Train_Coll_Points, Max_Targeted=Max_Targeted, Seed=Seed)
+        chunk = 1 if Num_Test_Coll_Points > 0 else 10
+        e = 0
+        while e < Num_Epochs:
+            m = min(chunk, Num_Epochs - e)
+            cap.run(m)
+            if Num_Test_Coll_Points > 0:
+                tp = [sample(i, Num_Epochs + e, Num_Test_Coll_Points).to(dev) for i in range(S)]
+                te = Testing(U_List, Xi, Mask, tp, Test_Inputs_List or Inputs_List, Test_Targets_List or Targets_List, Derivatives,
+                             LHS_Term, RHS_Terms, p, Weights)
+                hist["Test Coll"][e] = te["Coll Losses"]; hist["Test Data"][e] = te["Data Losses"]
+            if On_Epoch is not None or e + m >= Num_Epochs:
+                h = cap.history()
+                a = e + m - h["Lp"].shape[0]
+                for key in ("Train Coll", "Train Data", "Train Total", "L2", "Lp", "Num Targeted"):
+                    hist[key][a:e + m] = h[key]
+                if On_Epoch is not None:
+                    for q in range(e, e + m):
+                        On_Epoch(q, hist)
+            e += m
+        return hist
     for e in range(Num_Epochs):
         coll = [torch.vstack((sample(i, e, Num_Train_Coll_Points).to(dev), targeted[i])) for i in range(S)]
         tr = Training(U_List, Xi, Mask, coll, Inputs_List, Targets_List, Derivatives, LHS_Term, RHS_Terms, p, Weights, Optimizer,

@@ -22,3 +22,4 @@ from .engine import closure_total as Closure_Loss                          # noq
 from .Library_Reader import Read_Library, Parse_Term                        # noqa: F401
 from .Settings_Reader import Settings_Reader, Read_Error                     # noqa: F401
 from .Driver import (Update_Targeted_Points, Run_Epochs, Build_Mask, Threshold_Xi, Save_State, Load_State)   # noqa: F401
+from .Epoch_Graph import Captured_Epochs                                   # noqa: F401

@@ -36,7 +36,7 @@ class LaunchArgs(C.Structure):
                 ("inv_n", C.c_double), ("backward", C.c_int32), ("residual", C.c_void_p), ("features", C.c_void_p),
                 ("grad_params", C.c_void_p), ("grad_xi", C.c_void_p), ("stats", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("n_ctas", C.c_int32),
-                ("stream", C.c_void_p)]
+                ("stream", C.c_void_p), ("n_points_dev", C.c_void_p)]
 
 
 # every symbol include/pdelearn_b200.h declares, with its prototype
@@ -55,11 +55,18 @@ PROTOTYPES = {
                                       C.c_void_p, C.c_void_p]),
     "pdl_sample_points": (C.c_int, [C.POINTER(C.c_double), C.c_int32, C.c_int64, C.c_uint64, C.c_uint64,
                                     C.c_void_p, C.c_void_p]),
+    "pdl_sample_points_dev": (C.c_int, [C.POINTER(C.c_double), C.c_int32, C.c_int64, C.c_void_p, C.c_uint64,
+                                        C.c_void_p, C.c_void_p]),
     "pdl_abs_residual_moments": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pdl_select_targeted": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdl_targeted_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pdl_targeted_update_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                          C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pdl_adam_step_multi": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                      C.POINTER(C.c_int64), C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double,
+                                      C.c_void_p, C.c_void_p]),
     "pdl_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
                                 C.c_double, C.c_double, C.c_double, C.c_int64, C.c_void_p]),
     "pdl_axpby3": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_double,
@@ -87,7 +94,7 @@ def lib():
             fn = getattr(handle, name)            # AttributeError here = header/library mismatch
             fn.restype = res
             fn.argtypes = args
-        if handle.pdl_abi_version() != 1:
+        if handle.pdl_abi_version() != 2:
             raise NativeLibraryError("libpdelearn_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -435,8 +435,17 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
     float* sacc = bufZ + BUF;
     float* zs = BWD ? (P.zscratch + (size_t)gwarp * ZSCR) : nullptr;
     float* wp = BWD ? (P.wpriv + (size_t)gwarp * WPRIV) : nullptr;
-    const long long n_tiles = (P.n_points + 7) / 8;
-    const float two_inv_n = (float)(2.0 * P.inv_n);
+    // device-side row count (captured epochs: the number of targeted points changes from replay to replay)
+    long long NPTS = P.n_points;
+    double INVN = P.inv_n;
+    if (P.n_points_dev) {
+        NPTS = *P.n_points_dev;
+        if (NPTS < 0) NPTS = 0;
+        if (NPTS > P.n_points) NPTS = P.n_points;
+        INVN = NPTS > 0 ? 1.0 / (double)NPTS : 0.0;
+    }
+    const long long n_tiles = (NPTS + 7) / 8;
+    const float two_inv_n = (float)(2.0 * INVN);
 
     double lsum[PDL_NL], asum[PDL_NL];
     PDL_FOR_LANES { lsum[PDL_L] = 0.0; asum[PDL_L] = 0.0; }
@@ -454,9 +463,9 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
         PDL_FOR_LANES {
             const int pg = lane >> 2, g4 = lane & 3;
             const long long p = tile * 8 + pg;
-            valid[PDL_L] = (p < P.n_points) ? 1.f : 0.f;
+            valid[PDL_L] = (p < NPTS) ? 1.f : 0.f;
 #pragma unroll
-            for (int dd = 0; dd < D; ++dd) x[PDL_L][dd] = (p < P.n_points) ? P.points[p * D + dd] : 0.f;
+            for (int dd = 0; dd < D; ++dd) x[PDL_L][dd] = (p < NPTS) ? P.points[p * D + dd] : 0.f;
 #pragma unroll
             for (int i = 0; i < NPL; ++i) {
                 float z[J];
@@ -551,7 +560,7 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
             pdl_epilogue(u, sm + SM_XI, r, du, T);
             double rd = (double)r;
 #if PDL_MODE == 1
-            rd = (p < P.n_points) ? ((double)r - P.targets[p]) : 0.0;      // f32 prediction - f64 target (Loss.py:56-59)
+            rd = (p < NPTS) ? ((double)r - P.targets[p]) : 0.0;      // f32 prediction - f64 target (Loss.py:56-59)
             r = (float)rd;
 #endif
             const float v = valid[PDL_L];
@@ -566,7 +575,7 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
             }
             if (BWD) {
 #if PDL_MODE == 1
-                const float rs = (float)(2.0 * P.inv_n * rd) * v;
+                const float rs = (float)(2.0 * INVN * rd) * v;
 #else
                 const float rs = two_inv_n * r * v;
 #endif
@@ -965,6 +974,7 @@ struct ReduceArgs {
     float* grad_xi;          // [K]
     double* stats;           // [0] = mean loss (sum r^2 * inv_n), [1] = sum r^2, [2] = sum |r|
     double inv_n;
+    const long long* n_points_dev; long long capacity;
 };
 
 PDL_HD int prm_offset(int idx) {          // flat offset of parameter tensor idx
@@ -1026,7 +1036,9 @@ PDL_DEV void reduce_item(const ReduceArgs& R, int e) {
 PDL_DEV void reduce_stats(const ReduceArgs& R) {
     double s2 = 0.0, s1 = 0.0;
     for (int c = 0; c < R.n_ctas; ++c) { s2 += R.cta_stats[(size_t)c * 4]; s1 += R.cta_stats[(size_t)c * 4 + 1]; }
-    R.stats[0] = s2 * R.inv_n; R.stats[1] = s2; R.stats[2] = s1;
+    double inv_n = R.inv_n;
+    if (R.n_points_dev) { long long n = *R.n_points_dev; if (n > R.capacity) n = R.capacity; inv_n = n > 0 ? 1.0 / (double)n : 0.0; }
+    R.stats[0] = s2 * inv_n; R.stats[1] = s2; R.stats[2] = s1;
 }
 
 }  // namespace pdl
@@ -1085,6 +1097,7 @@ int pdl_k_launch(const pdl::Params* P, int n_ctas, int bwd, float* grad_params, 
     pdl::ReduceArgs R;
     R.cta_out = P->cta_out; R.cta_stats = P->cta_stats; R.n_ctas = n_ctas;
     R.grad_params = grad_params; R.grad_xi = grad_xi; R.stats = stats; R.inv_n = P->inv_n;
+    R.n_points_dev = P->n_points_dev; R.capacity = P->n_points;
     const int items = bwd ? pdl::REDUCE_ITEMS : 1;
     pdl_reduce_kernel<<<(items + 255) / 256, 256, 0, st>>>(R, bwd);
     return (int)cudaGetLastError();
@@ -1117,6 +1130,7 @@ int pdl_k_launch(const pdl::Params* P, int n_ctas, int bwd, float* grad_params, 
     pdl::ReduceArgs R;
     R.cta_out = P->cta_out; R.cta_stats = P->cta_stats; R.n_ctas = n_ctas;
     R.grad_params = grad_params; R.grad_xi = grad_xi; R.stats = stats; R.inv_n = P->inv_n;
+    R.n_points_dev = P->n_points_dev; R.capacity = P->n_points;
     if (bwd) for (int e = 0; e < pdl::REDUCE_ITEMS; ++e) pdl::reduce_item(R, e);
     pdl::reduce_stats(R);
     return 0;

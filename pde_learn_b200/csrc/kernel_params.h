@@ -15,4 +15,5 @@ struct PdlKernelParams {
     float* wpriv;                   // [n_warps][WPRIV]  per-warp weight-gradient partial sums
     float* cta_out;                 // [n_ctas][CTA_OUT] per-CTA gradient record
     double* cta_stats;              // [n_ctas][4]       sum r^2, sum |r|
+    const long long* n_points_dev;  // optional: row count read on the device (<= n_points = capacity); the mean then uses 1/rows
 };

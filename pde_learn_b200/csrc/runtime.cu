@@ -243,6 +243,7 @@ int pdl_loss_launch(pdl_plan* p, const pdl_launch_args* a) {
     }
     P.xi = a->xi; P.mask = a->mask; P.targets = a->targets; P.inv_n = a->inv_n;
     P.residual = a->residual; P.features = a->features;
+    P.n_points_dev = (const long long*)a->n_points_dev;
     char* w = (char*)(((uintptr_t)a->workspace + 255) & ~(uintptr_t)255);
     const size_t nw = (size_t)n_ctas * p->kinfo[9];
     P.zscratch = (float*)w; w += align256(nw * p->kinfo[2] * 4);
@@ -316,7 +317,9 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
     c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
 }
 struct SampleArgs { float lo[4]; float span[4]; float hi[4]; };
-__global__ void sample_kernel(const SampleArgs A, int d, long long n, unsigned long long seed, unsigned long long first, float* __restrict__ out) {
+__global__ void sample_kernel(const SampleArgs A, int d, long long n, unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
+                              unsigned long long first, float* __restrict__ out) {
+    if (seed_dev) seed = seed_dev[0];
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const unsigned long long idx = first + (unsigned long long)i;
@@ -357,15 +360,16 @@ __global__ void cutoff_kernel(const double* __restrict__ stats, long long n_rand
     if (var < 0.0) var = 0.0;
     out[0] = (float)(mean + 3.0 * sqrt(var));
 }
-__global__ void select_count_kernel(const float* __restrict__ r, long long n, float cutoff, const float* __restrict__ cutoff_dev,
-                                    int* __restrict__ counts) {
+__global__ void select_count_kernel(const float* __restrict__ r, long long n, const long long* __restrict__ n_dev, float cutoff,
+                                    const float* __restrict__ cutoff_dev, int* __restrict__ counts) {
     if (cutoff_dev) cutoff = cutoff_dev[0];
+    if (n_dev) { const long long m = n_dev[0]; n = m < n ? (m < 0 ? 0 : m) : n; }
     const long long i = (long long)blockIdx.x * 1024 + threadIdx.x;
     const int flag = (i < n && fabsf(r[i]) >= cutoff) ? 1 : 0;
     const int c = __syncthreads_count(flag);
     if (threadIdx.x == 0) counts[blockIdx.x] = c;
 }
-__global__ void select_scan_kernel(int* __restrict__ counts, int n_blocks, long long* __restrict__ total) {
+__global__ void select_scan_kernel(int* __restrict__ counts, int n_blocks, long long* __restrict__ total, long long cap) {
     // single block: exclusive scan of counts[0..n_blocks) in place, total to *total
     __shared__ long long carry;
     __shared__ int wsum[32];
@@ -391,12 +395,14 @@ __global__ void select_scan_kernel(int* __restrict__ counts, int n_blocks, long 
         if (threadIdx.x == 1023) carry = c0 + before + x;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *total = carry;
+    if (threadIdx.x == 0) *total = carry < cap ? carry : cap;
 }
-__global__ void select_scatter_kernel(const float* __restrict__ pts, const float* __restrict__ r, long long n, int d, float cutoff,
-                                      const float* __restrict__ cutoff_dev, const int* __restrict__ offsets, float* __restrict__ out) {
+__global__ void select_scatter_kernel(const float* __restrict__ pts, const float* __restrict__ r, long long n,
+                                      const long long* __restrict__ n_dev, int d, float cutoff, const float* __restrict__ cutoff_dev,
+                                      const int* __restrict__ offsets, float* __restrict__ out, long long cap) {
     __shared__ int wsum[32];
     if (cutoff_dev) cutoff = cutoff_dev[0];
+    if (n_dev) { const long long m = n_dev[0]; n = m < n ? (m < 0 ? 0 : m) : n; }
     const long long i = (long long)blockIdx.x * 1024 + threadIdx.x;
     const int flag = (i < n && fabsf(r[i]) >= cutoff) ? 1 : 0;
     const unsigned b = __ballot_sync(0xffffffffu, flag);
@@ -412,13 +418,36 @@ __global__ void select_scatter_kernel(const float* __restrict__ pts, const float
     __syncthreads();
     if (flag) {
         const long long dst = (long long)offsets[blockIdx.x] + (warp ? wsum[warp - 1] : 0) + within;
-        for (int j = 0; j < d; ++j) out[dst * d + j] = pts[i * d + j];
+        if (dst < cap) { for (int j = 0; j < d; ++j) out[dst * d + j] = pts[i * d + j]; }
     }
 }
 
 // ---- fused Adam (torch.optim.Adam, default flags) ----
 __global__ void adam_kernel(float* __restrict__ th, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             long long n, float lr_c, float b1, float b2, float inv_sqrt_c2, float eps) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float gi = g[i];
+        const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+        const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        th[i] -= lr_c * mi / (sqrtf(vi) * inv_sqrt_c2 + eps);
+    }
+}
+
+// same update over a table of tensors; the step count lives on the device (captured epochs: the bias corrections change per replay)
+#define PDL_ADAM_MAX_TENSORS 48
+struct AdamMultiArgs {
+    float* th[PDL_ADAM_MAX_TENSORS]; const float* g[PDL_ADAM_MAX_TENSORS]; float* m[PDL_ADAM_MAX_TENSORS]; float* v[PDL_ADAM_MAX_TENSORS];
+    long long n[PDL_ADAM_MAX_TENSORS];
+};
+__global__ void adam_multi_kernel(const AdamMultiArgs A, const float* __restrict__ step_dev, double lr, double b1d, double b2d, float eps) {
+    const int t = blockIdx.y;
+    const double step = (double)step_dev[0];
+    const double c1 = 1.0 - pow(b1d, step), c2 = 1.0 - pow(b2d, step);
+    const float lr_c = (float)(lr / c1), inv_sqrt_c2 = (float)(1.0 / sqrt(c2)), b1 = (float)b1d, b2 = (float)b2d;
+    float* th = A.th[t]; const float* g = A.g[t]; float* m = A.m[t]; float* v = A.v[t];
+    const long long n = A.n[t];
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const float gi = g[i];
@@ -477,7 +506,8 @@ int pdl_l2_squared_loss(const float* const* params, const int32_t* sizes, int32_
     return 0;
 }
 
-int pdl_sample_points(const double* bounds, int32_t d, int64_t n, uint64_t seed, uint64_t first, float* out, void* stream) {
+static int sample_points_impl(const double* bounds, int32_t d, int64_t n, uint64_t seed, const uint64_t* seed_dev, uint64_t first,
+                              float* out, void* stream) {
     if (d < 1 || d > 4 || !bounds || (n > 0 && !out)) return fail("bad sampler arguments");
     SampleArgs A;
     for (int j = 0; j < 4; ++j) { A.lo[j] = 0.f; A.span[j] = 0.f; A.hi[j] = 0.f; }
@@ -488,9 +518,16 @@ int pdl_sample_points(const double* bounds, int32_t d, int64_t n, uint64_t seed,
     if (n == 0) return 0;
     long long blocks = (n + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    sample_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(A, d, n, seed, first, out);
+    sample_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(A, d, n, seed, (const unsigned long long*)seed_dev, first, out);
     PDL_CUDA(cudaGetLastError());
     return 0;
+}
+int pdl_sample_points(const double* bounds, int32_t d, int64_t n, uint64_t seed, uint64_t first, float* out, void* stream) {
+    return sample_points_impl(bounds, d, n, seed, nullptr, first, out, stream);
+}
+int pdl_sample_points_dev(const double* bounds, int32_t d, int64_t n, const uint64_t* seed_dev, uint64_t first, float* out, void* stream) {
+    if (!seed_dev) return fail("seed_dev is null");
+    return sample_points_impl(bounds, d, n, 0, seed_dev, first, out, stream);
 }
 
 int pdl_abs_residual_moments(const float* residual, int64_t n, double* stats, void* stream) {
@@ -510,27 +547,37 @@ int pdl_select_targeted(const float* points, const float* residual, int64_t n, i
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { PDL_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int64_t), st)); return 0; }
     const int nb = (int)((n + 1023) / 1024);
-    select_count_kernel<<<nb, 1024, 0, st>>>(residual, n, cutoff, nullptr, block_scratch);
-    select_scan_kernel<<<1, 1024, 0, st>>>(block_scratch, nb, (long long*)out_count);
-    select_scatter_kernel<<<nb, 1024, 0, st>>>(points, residual, n, d, cutoff, nullptr, block_scratch, out_points);
+    select_count_kernel<<<nb, 1024, 0, st>>>(residual, n, nullptr, cutoff, nullptr, block_scratch);
+    select_scan_kernel<<<1, 1024, 0, st>>>(block_scratch, nb, (long long*)out_count, n);
+    select_scatter_kernel<<<nb, 1024, 0, st>>>(points, residual, n, nullptr, d, cutoff, nullptr, block_scratch, out_points, n);
     PDL_CUDA(cudaGetLastError());
     return 0;
 }
 
-int pdl_targeted_update(const float* points, const float* residual, int64_t n, int64_t n_random, int32_t d, float* out_points,
-                        int64_t* out_count, double* stats, int32_t* block_scratch, void* stream) {
-    if (!out_count || !block_scratch || !stats || n < 0 || n_random < 0 || n_random > n) return fail("bad arguments");
+static int targeted_update_impl(const float* points, const float* residual, int64_t n, const int64_t* n_dev, int64_t n_random, int32_t d,
+                                float* out_points, int64_t out_cap, int64_t* out_count, double* stats, int32_t* block_scratch, void* stream) {
+    if (!out_count || !block_scratch || !stats || n < 0 || n_random < 0 || n_random > n || out_cap < 0) return fail("bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { PDL_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int64_t), st)); return 0; }
     if (pdl_abs_residual_moments(residual, n_random, stats, stream)) return 1;
     float* cutoff_dev = reinterpret_cast<float*>(stats + 2);
     cutoff_kernel<<<1, 1, 0, st>>>(stats, n_random, cutoff_dev);
     const int nb = (int)((n + 1023) / 1024);
-    select_count_kernel<<<nb, 1024, 0, st>>>(residual, n, 0.f, cutoff_dev, block_scratch);
-    select_scan_kernel<<<1, 1024, 0, st>>>(block_scratch, nb, (long long*)out_count);
-    select_scatter_kernel<<<nb, 1024, 0, st>>>(points, residual, n, d, 0.f, cutoff_dev, block_scratch, out_points);
+    select_count_kernel<<<nb, 1024, 0, st>>>(residual, n, (const long long*)n_dev, 0.f, cutoff_dev, block_scratch);
+    select_scan_kernel<<<1, 1024, 0, st>>>(block_scratch, nb, (long long*)out_count, out_cap);
+    select_scatter_kernel<<<nb, 1024, 0, st>>>(points, residual, n, (const long long*)n_dev, d, 0.f, cutoff_dev, block_scratch, out_points, out_cap);
     PDL_CUDA(cudaGetLastError());
     return 0;
+}
+int pdl_targeted_update(const float* points, const float* residual, int64_t n, int64_t n_random, int32_t d, float* out_points,
+                        int64_t* out_count, double* stats, int32_t* block_scratch, void* stream) {
+    return targeted_update_impl(points, residual, n, nullptr, n_random, d, out_points, n, out_count, stats, block_scratch, stream);
+}
+int pdl_targeted_update_dev(const float* points, const float* residual, int64_t capacity, const int64_t* n_dev, int64_t n_random, int32_t d,
+                            float* out_points, int64_t out_capacity, int64_t* out_count, double* stats, int32_t* block_scratch,
+                            void* stream) {
+    if (!n_dev) return fail("n_dev is null");
+    return targeted_update_impl(points, residual, capacity, n_dev, n_random, d, out_points, out_capacity, out_count, stats, block_scratch, stream);
 }
 
 int pdl_adam_step(float* theta, const float* grad, float* m, float* v, int64_t n, double lr, double b1, double b2, double eps,
@@ -541,6 +588,25 @@ int pdl_adam_step(float* theta, const float* grad, float* m, float* v, int64_t n
     if (blocks > 148 * 8) blocks = 148 * 8;
     adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(theta, grad, m, v, n, (float)(lr / c1), (float)b1, (float)b2,
                                                                (float)(1.0 / sqrt(c2)), (float)eps);
+    PDL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int pdl_adam_step_multi(float* const* theta, const float* const* grad, float* const* m, float* const* v, const int64_t* sizes,
+                        int32_t n_tensors, double lr, double b1, double b2, double eps, const float* step_dev, void* stream) {
+    if (!theta || !grad || !m || !v || !sizes || !step_dev || n_tensors <= 0 || n_tensors > PDL_ADAM_MAX_TENSORS)
+        return fail("bad Adam arguments (at most 48 tensors per call)");
+    AdamMultiArgs A;
+    memset(&A, 0, sizeof A);
+    long long nmax = 0;
+    for (int t = 0; t < n_tensors; ++t) {
+        if (!theta[t] || !grad[t] || !m[t] || !v[t] || sizes[t] <= 0) return fail("bad Adam tensor");
+        A.th[t] = theta[t]; A.g[t] = grad[t]; A.m[t] = m[t]; A.v[t] = v[t]; A.n[t] = sizes[t];
+        if (sizes[t] > nmax) nmax = sizes[t];
+    }
+    long long bx = (nmax + 255) / 256;
+    if (bx > 148 * 4) bx = 148 * 4;
+    adam_multi_kernel<<<dim3((unsigned)bx, (unsigned)n_tensors), 256, 0, (cudaStream_t)stream>>>(A, step_dev, lr, b1, b2, (float)eps);
     PDL_CUDA(cudaGetLastError());
     return 0;
 }

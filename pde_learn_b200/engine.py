@@ -95,7 +95,7 @@ class Plan:
         return self._ws[idx], self._sm[idx]
 
     def launch(self, points, params, xi, mask, targets, inv_n, backward, residual, features, grad_params, grad_xi,
-               stats):
+               stats, n_points_dev=None):
         dev = points.device
         ws, n_sm = self.workspace(dev)
         arr = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
@@ -113,6 +113,7 @@ class Plan:
         a.stats = stats.data_ptr()
         a.workspace = ws.data_ptr(); a.workspace_bytes = ws.numel(); a.n_ctas = n_sm
         a.stream = torch.cuda.current_stream(dev).cuda_stream
+        a.n_points_dev = n_points_dev.data_ptr() if n_points_dev is not None else None   # device int64[1]: rows <= points.shape[0]
         with torch.cuda.device(dev):
             L.check(L.lib().pdl_loss_launch(self.handle, C.byref(a)))
 

@@ -59,6 +59,7 @@ def main(argv=None) -> Dict:
     ap.add_argument("--saves-dir", default=None, help="where save files live (default: <settings dir>/Saves)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--quiet", action="store_true")
+    ap.add_argument("--cuda-graph", action="store_true", help="replay each epoch as one captured CUDA graph (Adam only)")
     args = ap.parse_args(argv)
     root = os.path.dirname(os.path.abspath(args.settings))
     data_dir = args.data_dir or os.path.join(root, "Data", "DataSets")
@@ -114,7 +115,8 @@ def main(argv=None) -> Dict:
     hist = Run_Epochs(U_List, Xi, Mask, [D["Train Inputs"] for D in data], [D["Train Targets"] for D in data],
                       [D["Input Bounds"] for D in data], Derivs, LHS, RHS, S["p"], S["Weights"], opt, S["Num Epochs"],
                       S["Num Train Coll Points"], S["Num Test Coll Points"], [D["Test Inputs"] for D in data],
-                      [D["Test Targets"] for D in data], Seed=args.seed, On_Epoch=report)
+                      [D["Test Targets"] for D in data], Seed=args.seed, On_Epoch=report,
+                      Use_CUDA_Graph=bool(args.cuda_graph and S["Optimizer"] == "Adam"))
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     with torch.no_grad():                                              # masked components keep their initial value (main.py:419-423)

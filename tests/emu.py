@@ -23,7 +23,7 @@ class KernelParams(C.Structure):
     _fields_ = [("points", C.c_void_p), ("n_points", C.c_longlong), ("prm", C.c_void_p * 40), ("xi", C.c_void_p),
                 ("mask", C.c_void_p), ("targets", C.c_void_p), ("inv_n", C.c_double), ("residual", C.c_void_p),
                 ("features", C.c_void_p), ("zscratch", C.c_void_p), ("wpriv", C.c_void_p), ("cta_out", C.c_void_p),
-                ("cta_stats", C.c_void_p)]
+                ("cta_stats", C.c_void_p), ("n_points_dev", C.c_void_p)]
 
 
 def build_emu(desc):
