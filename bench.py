@@ -307,6 +307,23 @@ def run_ours(args):
                 "flops_per_point": plan.flops_per_point, "points_per_launch": B, "kernel_ms": k_ms,
                 "hbm_gbs_algorithmic": hbm_bytes / (k_ms * 1e-3) / 1e9,
                 "hbm_peak_gbs": peaks.get("hbm_gbs"), "traffic": traffic}
+    # the tensor-pipe view of the same launch: executed (3xTF32, padded) MMA flops against the measured mma.sync TF32 rate
+    try:
+        import re
+        src = L.plan_source(plan.desc)
+        df = {k: int(v) for k, v in re.findall(r"#define (PDL_WP|PDL_J|PDL_H|PDL_DGRAD_MMA|PDL_WGRAD_MMA) (\d+)", src)}
+        if "jet_mlp_kernel_mma.cuh" in src:
+            nt8, nm, nmt = df["PDL_WP"] // 8, (df["PDL_J"] + 1) // 2, (df["PDL_WP"] + 15) // 16
+            per_layer = 3 * nt8 * nt8 * nm * (1 + df["PDL_DGRAD_MMA"]) + 3 * nmt * nt8 * df["PDL_J"] * df["PDL_WGRAD_MMA"]
+            mma_flops_pt = per_layer * (df["PDL_H"] - 1) * (16 * 8 * 8 * 2) / 8.0
+            exe = mma_flops_pt * B / (k_ms * 1e-3) / 1e12
+            roofline["tensor_pipe"] = {"executed_tflops": exe, "peak": 277.0, "frac": exe / 277.0, "mma_per_tile_layer": per_layer,
+                                       "contractions_on_tensor_pipe": ["forward"] + (["dgrad"] if df["PDL_DGRAD_MMA"] else []) +
+                                                                      (["wgrad"] if df["PDL_WGRAD_MMA"] else []),
+                                       "peak_source": "mma.sync.m16n8k8 TF32 microbenchmark, profiles/r01_ubench.txt (277 TFLOP/s); "
+                                                      "3 MMAs per product (hi/lo split) and padding are executed, not algorithmic, flops"}
+    except Exception as ex:                                                  # informational only
+        roofline["tensor_pipe"] = {"error": str(ex)}
 
     # ---- end to end through the public API: pinned host points -> device, closure, loss back to host ----
     host_pts = [c.cpu().pin_memory() for c in coll]

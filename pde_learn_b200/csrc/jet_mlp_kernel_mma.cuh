@@ -989,9 +989,21 @@ PDL_HD int prm_offset(int idx) {          // flat offset of parameter tensor idx
 }
 constexpr int REDUCE_ITEMS = CTA_OUT;
 
+// The sum over CTAs is split into RED_Y interleaved partial sums (one per warp of a reduce block on the device) that are
+// combined in a fixed order: deterministic, and 8x shorter dependent chains than one serial loop over 148 records.
+constexpr int RED_Y = 8;
+PDL_DEV double reduce_partial(const ReduceArgs& R, int e, int y) {
+    double s = 0.0;
+    for (int c = y; c < R.n_ctas; c += RED_Y) s += (double)R.cta_out[(size_t)c * CTA_OUT + e];
+    return s;
+}
+PDL_DEV void reduce_store(const ReduceArgs& R, int e, double s);
 PDL_DEV void reduce_item(const ReduceArgs& R, int e) {
     double s = 0.0;
-    for (int c = 0; c < R.n_ctas; ++c) s += (double)R.cta_out[(size_t)c * CTA_OUT + e];
+    for (int y = 0; y < RED_Y; ++y) s += reduce_partial(R, e, y);
+    reduce_store(R, e, s);
+}
+PDL_DEV void reduce_store(const ReduceArgs& R, int e, double s) {
     const float v = (float)s;
     if (e < WPRIV) {
         const int l = e / WPRIV_LAYER + 1;                   // hidden->hidden layer index 1..H-1
@@ -1062,10 +1074,22 @@ __global__ void __launch_bounds__(pdl::NT, 1) pdl_main_kernel(const pdl::Params 
     pdl::cta_tail_thread(P, sm, blockIdx.x, tid, BWD);
 }
 
-__global__ void pdl_reduce_kernel(const pdl::ReduceArgs R, int with_grads) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (with_grads && e < pdl::REDUCE_ITEMS) pdl::reduce_item(R, e);
-    if (e == 0) pdl::reduce_stats(R);
+// block = 32 items x RED_Y partial sums: warp y adds the records c = y, y + RED_Y, ... (coalesced 128-byte rows)
+__global__ void __launch_bounds__(32 * pdl::RED_Y) pdl_reduce_kernel(const pdl::ReduceArgs R, int with_grads) {
+    __shared__ double part[pdl::RED_Y][32];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int e = blockIdx.x * 32 + x;
+    if (with_grads) {
+        part[y][x] = (e < pdl::REDUCE_ITEMS) ? pdl::reduce_partial(R, e, y) : 0.0;
+        __syncthreads();
+        if (y == 0 && e < pdl::REDUCE_ITEMS) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < pdl::RED_Y; ++q) s += part[q][x];
+            pdl::reduce_store(R, e, s);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) pdl::reduce_stats(R);
 }
 
 extern "C" {
@@ -1099,7 +1123,7 @@ int pdl_k_launch(const pdl::Params* P, int n_ctas, int bwd, float* grad_params, 
     R.grad_params = grad_params; R.grad_xi = grad_xi; R.stats = stats; R.inv_n = P->inv_n;
     R.n_points_dev = P->n_points_dev; R.capacity = P->n_points;
     const int items = bwd ? pdl::REDUCE_ITEMS : 1;
-    pdl_reduce_kernel<<<(items + 255) / 256, 256, 0, st>>>(R, bwd);
+    pdl_reduce_kernel<<<(items + 31) / 32, 32 * pdl::RED_Y, 0, st>>>(R, bwd);
     return (int)cudaGetLastError();
 }
 }

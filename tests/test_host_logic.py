@@ -168,3 +168,22 @@ def test_save_load_state_round_trip(tmp_path):
     assert str(st["LHS Term"]) == str(lhs) and [str(t) for t in st["RHS Terms"]] == [str(t) for t in rhs]
     assert P.Threshold_Xi(torch.tensor([0.1, 1e-4, -0.2]), torch.tensor([False, False, True])) == [0]
     assert P.Build_Mask(torch.tensor([0.1, 1e-4, -0.2])).tolist() == [False, True, False]
+
+
+@pytest.mark.parametrize("dim,args", [("1d", (0.25, 120, 40)), ("2d", (0.25, 90, 30))])
+def test_dataset_preparation_matches_reference_files(dim, args, tmp_path):
+    """Data_Sets.From_MATLAB_* writes, bit for bit, the file the reference's Data/From_MATLAB.py wrote from the same .mat with the
+    same numpy seed (fixtures: tests/golden/make_golden_dataset.py)."""
+    import os
+    import numpy as np
+    from pde_learn_b200 import Data_Sets
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    f = Data_Sets.From_MATLAB_1D if dim == "1d" else Data_Sets.From_MATLAB_2D
+    path = f(os.path.join(gold, "synthetic_%s.mat" % dim), *args, Directory=str(tmp_path), Seed=11)
+    assert os.path.basename(path) == "synthetic_%s_N25_P%d.npz" % (dim, args[1])
+    got, want = np.load(path), np.load(os.path.join(gold, "dataset_%s.npz" % dim))
+    assert sorted(got.files) == sorted(want.files)
+    for k in want.files:
+        assert got[k].dtype == want[k].dtype and got[k].shape == want[k].shape, k
+        assert np.array_equal(got[k], want[k]), k
+    assert Data_Sets.From_MATLAB(os.path.join(gold, "synthetic_%s.mat" % dim), *args, Directory=str(tmp_path), Seed=11) == path
