@@ -332,7 +332,7 @@ PDL_DEV void stage_thread2(const Params& P, float* sm, int tid) {
 // ---------------------------------------------------------------------------------------------
 // the per-warp tile loop
 // ---------------------------------------------------------------------------------------------
-template <bool BWD>
+template <bool BWD, bool DEVN>
 PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, int n_warps
 #ifndef PDL_EMULATE
                        , const int lane
@@ -344,9 +344,11 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
     float* zs = BWD ? (P.zscratch + (size_t)gwarp * ZSCR) : nullptr;
     float* wp = BWD ? (P.wpriv + (size_t)gwarp * WPRIV) : nullptr;
     // device-side row count (captured epochs: the number of targeted points changes from replay to replay)
+    // (a separate instantiation: with the count in a kernel parameter the compiler keeps it in the constant bank, with the count
+    // loaded from memory it costs four live registers in a kernel that has none to spare -- measured 8 % on heat)
     long long NPTS = P.n_points;
     double INVN = P.inv_n;
-    if (P.n_points_dev) {
+    if (DEVN) {
         NPTS = *P.n_points_dev;
         if (NPTS < 0) NPTS = 0;
         if (NPTS > P.n_points) NPTS = P.n_points;
@@ -792,7 +794,7 @@ PDL_DEV void reduce_stats(const ReduceArgs& R) {
 // =============================================================================================
 #ifndef PDL_EMULATE
 
-template <bool BWD>
+template <bool BWD, bool DEVN>
 __global__ void __launch_bounds__(pdl::NT, 1) pdl_main_kernel(const pdl::Params P) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x;
@@ -801,7 +803,7 @@ __global__ void __launch_bounds__(pdl::NT, 1) pdl_main_kernel(const pdl::Params 
     pdl::stage_thread2(P, sm, tid);
     __syncthreads();
     const int warp = tid >> 5;
-    pdl::warp_body<BWD>(P, sm, warp, blockIdx.x * pdl::NW + warp, gridDim.x * pdl::NW, tid & 31);
+    pdl::warp_body<BWD, DEVN>(P, sm, warp, blockIdx.x * pdl::NW + warp, gridDim.x * pdl::NW, tid & 31);
     __syncthreads();
     pdl::cta_tail_thread(P, sm, blockIdx.x, tid, BWD);
 }
@@ -840,14 +842,21 @@ int pdl_k_launch(const pdl::Params* P, int n_ctas, int bwd, float* grad_params, 
     cudaError_t e0 = cudaGetDevice(&dev);
     if (e0 != cudaSuccess) return (int)e0;
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(pdl_main_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pdl::SM_TOTAL * 4);
+        cudaError_t e = cudaFuncSetAttribute(pdl_main_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pdl::SM_TOTAL * 4);
         if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(pdl_main_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pdl::SM_TOTAL * 4);
+        e = cudaFuncSetAttribute(pdl_main_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pdl::SM_TOTAL * 4);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(pdl_main_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pdl::SM_TOTAL * 4);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(pdl_main_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pdl::SM_TOTAL * 4);
         if (e != cudaSuccess) return (int)e;
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
-    if (bwd) pdl_main_kernel<true><<<n_ctas, pdl::NT, pdl::SM_TOTAL * 4, st>>>(*P);
-    else pdl_main_kernel<false><<<n_ctas, pdl::NT, pdl::SM_TOTAL * 4, st>>>(*P);
+    const bool devn = P->n_points_dev != nullptr;
+    if (bwd && !devn) pdl_main_kernel<true, false><<<n_ctas, pdl::NT, pdl::SM_TOTAL * 4, st>>>(*P);
+    else if (bwd) pdl_main_kernel<true, true><<<n_ctas, pdl::NT, pdl::SM_TOTAL * 4, st>>>(*P);
+    else if (!devn) pdl_main_kernel<false, false><<<n_ctas, pdl::NT, pdl::SM_TOTAL * 4, st>>>(*P);
+    else pdl_main_kernel<false, true><<<n_ctas, pdl::NT, pdl::SM_TOTAL * 4, st>>>(*P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     pdl::ReduceArgs R;
@@ -878,8 +887,11 @@ int pdl_k_launch(const pdl::Params* P, int n_ctas, int bwd, float* grad_params, 
         for (int tid = 0; tid < pdl::NT; ++tid) pdl::stage_thread(*P, sm, tid);
         for (int tid = 0; tid < pdl::NT; ++tid) pdl::stage_thread2(*P, sm, tid);
         for (int w = 0; w < pdl::NW; ++w) {
-            if (bwd) pdl::warp_body<true>(*P, sm, w, cta * pdl::NW + w, n_ctas * pdl::NW);
-            else pdl::warp_body<false>(*P, sm, w, cta * pdl::NW + w, n_ctas * pdl::NW);
+            const bool devn = P->n_points_dev != nullptr;
+            if (bwd && devn) pdl::warp_body<true, true>(*P, sm, w, cta * pdl::NW + w, n_ctas * pdl::NW);
+            else if (bwd) pdl::warp_body<true, false>(*P, sm, w, cta * pdl::NW + w, n_ctas * pdl::NW);
+            else if (devn) pdl::warp_body<false, true>(*P, sm, w, cta * pdl::NW + w, n_ctas * pdl::NW);
+            else pdl::warp_body<false, false>(*P, sm, w, cta * pdl::NW + w, n_ctas * pdl::NW);
         }
         for (int tid = 0; tid < pdl::NT; ++tid) pdl::cta_tail_thread(*P, sm, cta, tid, bwd != 0);
     }

@@ -51,7 +51,7 @@ def ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-def run_emu(desc, points, params, xi, mask, inv_n=None, backward=True, targets=None, n_ctas=2):
+def run_emu(desc, points, params, xi, mask, inv_n=None, backward=True, targets=None, n_ctas=2, rows_dev=None):
     """Returns dict(loss, sum_r2, residual, features, grad_params(flat), grad_xi)."""
     lib, _ = build_emu(desc)
     info = (C.c_int * 16)()
@@ -85,6 +85,8 @@ def run_emu(desc, points, params, xi, mask, inv_n=None, backward=True, targets=N
     zs_a, wp_a = al(zs), al(wp)
     P.zscratch = ptr(zs_a); P.wpriv = ptr(wp_a); P.cta_out = ptr(co); P.cta_stats = ptr(cs)
     gp = np.full(nscal, np.nan, np.float32); gx = np.full(max(1, K), np.nan, np.float32); st = np.zeros(4, np.float64)
+    cnt = np.array([int(rows_dev)], dtype=np.int64) if rows_dev is not None else None     # pdl_launch_args.n_points_dev
+    P.n_points_dev = ptr(cnt)
     rc = lib.pdl_k_launch(C.byref(P), n_ctas, 1 if backward else 0, ptr(gp), ptr(gx), ptr(st), None)
     assert rc == 0
     return {"loss": st[0], "sum_r2": st[1], "sum_abs": st[2], "residual": resid, "features": feats,

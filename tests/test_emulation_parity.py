@@ -120,3 +120,21 @@ def test_emulated_engines_explicitly(name, engine, dgrad, wgrad, monkeypatch):
     assert rel_max(out["residual"], resid.detach().numpy()) <= TOL
     assert rel_max(out["grad_params"], np.concatenate([x.numpy().ravel() for x in og[:-1]])) <= TOL
     assert rel_max(out["grad_xi"], og[-1].numpy()) <= TOL
+
+
+@pytest.mark.parametrize("name", ["heat_tanh", "ks_rational"])
+def test_emulated_device_row_count(name):
+    """The row count read from memory (pdl_launch_args.n_points_dev, captured epochs): a launch over the whole buffer with the count
+    37 equals the launch over the first 37 rows; rows beyond the count are not touched and the mean uses 1/37."""
+    g = GoldenCase(name)
+    desc, keep = desc_for(g)
+    P = g.points.numpy()[:60]
+    args = ([p.numpy() for p in g.params], g.xi.numpy(), np.array(g.mask, dtype=np.uint8))
+    a = emu.run_emu(desc, P[:37], *args)
+    b = emu.run_emu(desc, P, *args, inv_n=123.0, rows_dev=37)
+    assert np.array_equal(a["residual"], b["residual"][:37]) and np.isnan(b["residual"][37:]).all()
+    assert a["loss"] == b["loss"]
+    assert np.array_equal(a["grad_params"], b["grad_params"]) and np.array_equal(a["grad_xi"], b["grad_xi"])
+    c = emu.run_emu(desc, P, *args, rows_dev=1000)               # a count above the capacity is clamped
+    d = emu.run_emu(desc, P, *args)
+    assert c["loss"] == d["loss"] and np.array_equal(c["grad_params"], d["grad_params"])
