@@ -49,7 +49,9 @@ constexpr int SB = (JB > 0) ? pad_stride(WP * JB) : 0;
 constexpr int SF = WP;                      // row stride of the fragment-ordered weight copies (rows 8 banks apart for WP = 40)
 constexpr int NT8 = WP / 8;                 // 8-wide neuron tiles (MMA n-tiles and k-steps)
 constexpr int NM = (J + 1) / 2;             // component pairs = m16 row blocks per neuron tile
-constexpr bool DGRAD_MMA = (PDL_DGRAD_MMA != 0);   // data gradient on the tensor pipe too (two more weight copies)
+constexpr bool DGRAD_MMA = (PDL_DGRAD_MMA != 0);   // data gradient on the tensor pipe too
+constexpr bool DGRAD_T = (PDL_DGRAD_MMA == 1);     // ... with its B fragments from W^T hi/lo copies (conflict-free LDS.64); mode 2 reads
+                                                   // them from the forward copies instead (two LDS.32, 2-way conflicts, no extra memory)
 constexpr bool WGRAD_MMA = (PDL_WGRAD_MMA != 0);   // weight gradient on the tensor pipe (k = the tile's 8 points, one k-step per component)
 constexpr int NMT = (WP + 15) / 16;         // m16 tiles over the output neurons of a weight-gradient block
 constexpr int NFRAG = NMT * NT8;            // C fragments of one layer's weight gradient
@@ -87,7 +89,7 @@ constexpr int SM_HH = (SM_B0 + WP + 3) / 4 * 4;              // per hidden->hidd
 // per hidden->hidden layer: W hi/lo [n][k] (forward B fragments), then either W^T hi/lo [k][n] (dgrad B fragments) or the
 // FP32-pipe dgrad copy Wd[n][t][i]; bias
 constexpr int HH_WHI = 0, HH_WLO = WP * SF, HH_THI = 2 * WP * SF, HH_TLO = 3 * WP * SF, HH_WD = 2 * WP * SF;
-constexpr int HH_B = DGRAD_MMA ? 4 * WP * SF : (2 * WP * SF + WP * SD);
+constexpr int HH_B = DGRAD_T ? 4 * WP * SF : (DGRAD_MMA ? 2 * WP * SF : (2 * WP * SF + WP * SD));
 constexpr int HH_SIZE = (HH_B + WP + 3) / 4 * 4;
 constexpr int SM_WH = SM_HH + NHH * HH_SIZE;
 constexpr int SM_BH = SM_WH + WP;
@@ -394,10 +396,10 @@ PDL_DEV void stage_thread2(const Params& P, float* sm, int tid) {
             const uint32_t uh = tf32_rna(w), ul = tf32_rna(w - u2f(uh));   // staged once per CTA: round the low part too
             base[HH_WHI + n * SF + k] = u2f(uh);
             base[HH_WLO + n * SF + k] = u2f(ul);
-            if (DGRAD_MMA) {
+            if (DGRAD_T) {
                 base[HH_THI + k * SF + n] = u2f(uh);
                 base[HH_TLO + k * SF + n] = u2f(ul);
-            } else {
+            } else if (!DGRAD_MMA) {
                 // FP32-pipe dgrad copy grouped by the lane column that owns input neuron k: t = (k%8)/2, i = 2*(k/8) + k%2
                 base[HH_WD + n * SD + ((k & 7) >> 1) * GS + 2 * (k >> 3) + (k & 1)] = w;
             }
@@ -823,6 +825,8 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                 // ---- data gradient on the tensor pipe: hb = zb W, A fragments straight from the registers, B = W^T hi/lo
                 const float* Thi = sm + SM_HH + (l - 1) * HH_SIZE + HH_THI;
                 const float* Tlo = sm + SM_HH + (l - 1) * HH_SIZE + HH_TLO;
+                const float* Whi_ = sm + SM_HH + (l - 1) * HH_SIZE + HH_WHI;
+                const float* Wlo_ = sm + SM_HH + (l - 1) * HH_SIZE + HH_WLO;
                 float hbfr[NT8][NM][PDL_NL][4];
                 PDL_FOR_LANES {
 #pragma unroll
@@ -851,9 +855,15 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                         uint32_t bhi[PDL_NL][2], blo[PDL_NL][2];
                         PDL_FOR_LANES {
                             const int g = lane >> 2, t = lane & 3;
-                            const pdl_f2 vh = ld2(Thi + (8 * q + g) * SF + 8 * s + 2 * t);
-                            const pdl_f2 vl = ld2(Tlo + (8 * q + g) * SF + 8 * s + 2 * t);
-                            bhi[PDL_L][0] = f2u(vh.x); bhi[PDL_L][1] = f2u(vh.y); blo[PDL_L][0] = f2u(vl.x); blo[PDL_L][1] = f2u(vl.y);
+                            if (DGRAD_T) {
+                                const pdl_f2 vh = ld2(Thi + (8 * q + g) * SF + 8 * s + 2 * t);
+                                const pdl_f2 vl = ld2(Tlo + (8 * q + g) * SF + 8 * s + 2 * t);
+                                bhi[PDL_L][0] = f2u(vh.x); bhi[PDL_L][1] = f2u(vh.y); blo[PDL_L][0] = f2u(vl.x); blo[PDL_L][1] = f2u(vl.y);
+                            } else {                            // B[n][k] = W[n][k] straight from the forward copies
+                                const int o = (8 * s + 2 * t) * SF + 8 * q + g;
+                                bhi[PDL_L][0] = f2u(Whi_[o]); bhi[PDL_L][1] = f2u(Whi_[o + SF]);
+                                blo[PDL_L][0] = f2u(Wlo_[o]); blo[PDL_L][1] = f2u(Wlo_[o + SF]);
+                            }
                         }
 #pragma unroll
                         for (int m = 0; m < NM; ++m) {

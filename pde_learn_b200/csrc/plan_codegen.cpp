@@ -134,7 +134,7 @@ int smem_floats(const PlanMeta& m, int nw) {
         const int SO_XI = WP * D + WP + WP + 1 + 7 * H;
         const int SACC = (SO_XI + KX * TP + 3) / 4 * 4;
         const int SM_HH = (WP * D + WP + 3) / 4 * 4;
-        const int HH_B = m.dgrad_mma ? 4 * WP * SF : (2 * WP * SF + WP * SD);
+        const int HH_B = (m.dgrad_mma == 1) ? 4 * WP * SF : (m.dgrad_mma ? 2 * WP * SF : (2 * WP * SF + WP * SD));
         const int HH_SIZE = (HH_B + WP + 3) / 4 * 4;
         const int SM_WH = SM_HH + NHH * HH_SIZE;
         const int SM_RAT = (SM_WH + WP + 1 + 3) / 4 * 4;
@@ -230,8 +230,14 @@ std::string generate_plan_source(const PlanSpec& spec, PlanMeta* meta_out) {
     meta.engine = spec.engine >= 0 ? spec.engine : ((H >= 2) ? 1 : 0);
     if (meta.engine == 1) {
         meta.tile_points = 8;
-        meta.dgrad_mma = (spec.dgrad_mma == 0) ? 0 : ((spec.dgrad_mma == 1 || WP <= 48) ? 1 : 0);   // wide nets would spill
-        if (smem_floats(meta, nw) * 4 > 227 * 1024) meta.dgrad_mma = 0;     // fall back to the FP32-pipe data gradient (one weight copy less)
+        // data gradient on the tensor pipe: 1 = B fragments from W^T hi/lo copies (needs four weight copies in shared memory),
+        // 2 = B fragments from the forward copies (no extra memory, 2-way bank conflicts); wide nets would spill either way
+        if (spec.dgrad_mma >= 0) meta.dgrad_mma = spec.dgrad_mma;
+        else {
+            meta.dgrad_mma = (WP <= 48) ? 1 : 0;
+            if (meta.dgrad_mma == 1 && smem_floats(meta, nw) * 4 > 227 * 1024) meta.dgrad_mma = 2;
+        }
+        if (meta.dgrad_mma == 1 && smem_floats(meta, nw) * 4 > 227 * 1024) meta.dgrad_mma = 2;
         // weight gradient on the tensor pipe: measured faster everywhere except Rational nets that also run the data gradient there
         // (register pressure; heat 5.44 -> 5.81 ms, burgers 7.08 -> 7.74 ms), see experiments/README.md
         meta.wgrad_mma = (spec.wgrad_mma >= 0) ? (spec.wgrad_mma ? 1 : 0) : ((spec.activation == 1 && meta.dgrad_mma) ? 0 : 1);

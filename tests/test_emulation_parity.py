@@ -100,6 +100,7 @@ def test_emulated_sharded_inv_n_is_additive():
     ("heat_tanh", "mma", "1", "0"), ("heat_rational", "mma", "0", "0"), ("kdv_tanh", "mma", "1", "0"), ("wave_mixed_tanh", "mma", "0", "0"),
     ("heat_tanh", "mma", "1", "1"), ("heat_rational", "mma", "0", "1"), ("kdv_tanh", "mma", "1", "1"), ("ks_tanh", "mma", "0", "1"),
     ("burgers_rational20", "mma", "1", "1"), ("heat3d_tanh", "mma", "0", "1"), ("rd2d_tanh", "mma", "0", "1"),
+    ("ks_tanh", "mma", "2", "1"), ("ks_rational", "mma", "2", "0"), ("heat_tanh", "mma", "2", "1"), ("heat3d_tanh", "mma", "2", "1"),
     ("heat_tanh", "ffma", "0", "0"), ("ks_rational", "ffma", "0", "0"), ("rd2d_tanh", "ffma", "0", "0"), ("burgers_rational20", "ffma", "0", "0")])
 def test_emulated_engines_explicitly(name, engine, dgrad, wgrad, monkeypatch):
     """Both kernel families by explicit choice: the tensor-pipe engine (jet_mlp_kernel_mma.cuh, mma.sync.m16n8k8 modelled
