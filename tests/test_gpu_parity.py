@@ -191,6 +191,55 @@ def test_full_size_properties_heat_1m():
     assert float((0.5 * (r0 + r1) - rh).abs().max()) <= 1e-5 * float(r1.abs().max())
 
 
+@pytest.mark.parametrize("workload,act,N", [("ks", "Tanh", 1 << 21), ("rd2d", "Rational", 1 << 20), ("kdv", "Tanh", 1 << 21)])
+def test_full_size_properties_other_configs(workload, act, N):
+    """The per-GPU shares of configs 3-5 (KS: 2^21 of 16 M rows on 8 GPUs; KdV: 2^21; 2-D reaction-diffusion with Rational): the
+    size-independent properties the sharded path relies on -- determinism, shard additivity with 1/N_global, loss = mean r^2 --
+    and a spot check of 2048 of those rows against the float64 oracle."""
+    import pde_learn_b200 as P
+    from pde_learn_b200 import configs
+    torch.manual_seed(1)
+    d, bounds, derivs, lhs, rhs = configs.config(workload)
+    U = P.Network([d] + [40] * 5 + [1], act, Device=_dev())
+    K = len(rhs)
+    xi = (0.1 * torch.randn(K)).to(_dev()).requires_grad_(True)
+    mask = torch.zeros(K, dtype=torch.bool); mask[2] = True
+    pts = P.Generate_Points(bounds, N, _dev(), Seed=4)
+
+    def run(p, inv_n):
+        for q in U.parameters():
+            q.grad = None
+        xi.grad = None
+        l, r = P.Coll_Loss(U, xi, mask, p, derivs, lhs, rhs, Inv_N=inv_n)
+        l.backward()
+        return float(l), r, torch.cat([q.grad.reshape(-1) for q in U.parameters()] + [xi.grad])
+
+    l_all, r_all, g_all = run(pts, 1.0 / N)
+    l_again, r_again, g_again = run(pts, 1.0 / N)
+    assert l_all == l_again and torch.equal(r_all, r_again) and torch.equal(g_all, g_again)
+    q4 = N // 4
+    parts = [run(pts[i * q4:(i + 1) * q4], 1.0 / N) for i in range(4)]
+    assert abs(sum(p[0] for p in parts) - l_all) <= 2e-6 * abs(l_all)
+    assert torch.equal(torch.cat([p[1] for p in parts]), r_all)
+    assert float((sum(p[2] for p in parts) - g_all).abs().max()) <= 3e-6 * float(g_all.abs().max())
+    assert abs(l_all - float((r_all.double() ** 2).mean())) <= 1e-6 * abs(l_all)
+    assert float(xi.grad[2]) == 0.0
+    # spot check against the oracle on a slice of the same rows
+    sl = pts[N // 2:N // 2 + 2048]
+    l_s, r_s, g_s = run(sl, 1.0 / 2048)
+    _, lhs_o, rhs_o, _ = O.config_library(workload)
+    ra = [a.a.detach().cpu() for a in list(U.Activation_Functions)[:-1]] if act == "Rational" else []
+    rb = [a.b.detach().cpu() for a in list(U.Activation_Functions)[:-1]] if act == "Rational" else []
+    net = O.NetParams([l.weight.detach().cpu() for l in U.Layers], [l.bias.detach().cpu() for l in U.Layers],
+                      act.lower(), ra, rb).to(torch.float64, True)
+    xo = xi.detach().cpu().double().requires_grad_(True)
+    lo, ro, _ = O.coll_loss(lambda X: O.mlp_forward(net, X), xo, mask.tolist(), sl.cpu().double(), lhs_o, rhs_o)
+    go = torch.autograd.grad(lo, net.tensors() + [xo])
+    assert abs(l_s - float(lo)) <= TOL * float(lo)
+    assert rel_max(r_s.cpu().numpy(), ro.detach().numpy()) <= TOL
+    assert rel_max(g_s.cpu().numpy(), np.concatenate([x.numpy().ravel() for x in go])) <= TOL
+
+
 def test_training_step_vs_reference_golden():
     """One Adam step of Training() (two data sets sharing Xi, one masked term) vs the reference's own step."""
     import pde_learn_b200 as P
