@@ -55,7 +55,8 @@ def Training(U_List: List, Xi: torch.Tensor, Mask: torch.Tensor, Coll_Points_Lis
     assert len(U_List) == len(Targets_List)
     S = len(U_List)
     for U in U_List:
-        U.train()
+        if not U.training:            # Module.train() walks every submodule; skip the walk when nothing changes
+            U.train()
     world = 1
     if Process_Group is not None:
         import torch.distributed as dist
@@ -110,7 +111,8 @@ def Testing(U_List: List, Xi: torch.Tensor, Mask: torch.Tensor, Coll_Points_List
     assert len(U_List) == len(Targets_List)
     S = len(U_List)
     for U in U_List:
-        U.eval()
+        if U.training:
+            U.eval()
     with torch.no_grad():
         vals = [Lp_Loss(Xi=Xi, Mask=Mask, p=p).to(torch.float64)]
         for i in range(S):
