@@ -52,6 +52,14 @@ constexpr int NM = (J + 1) / 2;             // component pairs = m16 row blocks 
 constexpr bool DGRAD_MMA = (PDL_DGRAD_MMA != 0);   // data gradient on the tensor pipe too
 constexpr bool DGRAD_T = (PDL_DGRAD_MMA == 1);     // ... with its B fragments from W^T hi/lo copies (conflict-free LDS.64); mode 2 reads
                                                    // them from the forward copies instead (two LDS.32, 2-way conflicts, no extra memory)
+#ifndef PDL_CROSS_BF16
+#define PDL_CROSS_BF16 0
+#endif
+// XBF: the two cross terms lo*Bhi + hi*Blo of a split product run as ONE bf16 m16n8k16 MMA (k slots 0-7 carry lo(x) against
+// bf16(W), slots 8-15 carry bf16(x) against lo(W)); with the TF32 hi*hi MMA that is 2 instead of 3 tensor-pipe instructions per
+// product.  The cross terms are 2^-12 of the product, so bf16's 2^-9 rounding leaves an error of ~2^-21 per product.
+// PDL_CROSS_BF16 is a bit mask: 1 = forward, 2 = data gradient, 4 = weight gradient.
+constexpr bool XBF_F = (PDL_CROSS_BF16 & 1) != 0, XBF_D = (PDL_CROSS_BF16 & 2) != 0, XBF_W = (PDL_CROSS_BF16 & 4) != 0;
 constexpr bool WGRAD_MMA = (PDL_WGRAD_MMA != 0);   // weight gradient on the tensor pipe (k = the tile's 8 points, one k-step per component)
 constexpr int NMT = (WP + 15) / 16;         // m16 tiles over the output neurons of a weight-gradient block
 constexpr int NFRAG = NMT * NT8;            // C fragments of one layer's weight gradient
@@ -88,8 +96,12 @@ constexpr int SM_B0 = SM_W0 + WP * D;
 constexpr int SM_HH = (SM_B0 + WP + 3) / 4 * 4;              // per hidden->hidden layer: Wf, Wd, bias
 // per hidden->hidden layer: W hi/lo [n][k] (forward B fragments), then either W^T hi/lo [k][n] (dgrad B fragments) or the
 // FP32-pipe dgrad copy Wd[n][t][i]; bias
-constexpr int HH_WHI = 0, HH_WLO = WP * SF, HH_THI = 2 * WP * SF, HH_TLO = 3 * WP * SF, HH_WD = 2 * WP * SF;
-constexpr int HH_B = DGRAD_T ? 4 * WP * SF : (DGRAD_MMA ? 2 * WP * SF : (2 * WP * SF + WP * SD));
+// With XBF the "lo" planes hold the packed bf16 cross operands instead: word (n, 2j) = {bf16 W[n][2j], bf16 W[n][2j+1]}, word
+// (n, 2j+1) = {bf16 lo(W[n][2j]), bf16 lo(W[n][2j+1])} -- one LDS.64 per B fragment, as before.  Mode 2 then needs the transposed
+// cross plane as its third plane (HH_THI is unused there).
+constexpr int HH_WHI = 0, HH_WLO = WP * SF, HH_THI = 2 * WP * SF, HH_TLO = DGRAD_T ? 3 * WP * SF : 2 * WP * SF, HH_WD = 2 * WP * SF;
+constexpr int HH_B = DGRAD_T ? 4 * WP * SF : (DGRAD_MMA ? ((XBF_D ? 3 : 2) * WP * SF) : (2 * WP * SF + WP * SD));
+static_assert(!(XBF_F && DGRAD_MMA && !DGRAD_T && !XBF_D), "mode-2 data gradient reads the TF32 lo plane the bf16 forward replaces");
 constexpr int HH_SIZE = (HH_B + WP + 3) / 4 * 4;
 constexpr int SM_WH = SM_HH + NHH * HH_SIZE;
 constexpr int SM_BH = SM_WH + WP;
@@ -255,6 +267,56 @@ PDL_DEV void split_tf32_dg(float x, uint32_t& hi, uint32_t& lo) {
     split_tf32_raw(x, hi, lo);
 #endif
 }
+// two FP32 values -> packed bf16x2, round to nearest even; `k0` lands in the low half (the lower k index of an MMA fragment)
+PDL_DEV uint32_t pack_bf16(float k0, float k1) {
+#ifdef PDL_EMULATE
+    const uint32_t a = f2u(k0), b = f2u(k1);
+    const uint32_t ra = (a + 0x7FFFu + ((a >> 16) & 1u)) >> 16, rb = (b + 0x7FFFu + ((b >> 16) & 1u)) >> 16;
+    return (rb << 16) | (ra & 0xFFFFu);
+#else
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(k1), "f"(k0));
+    return r;
+#endif
+}
+// A-operand registers of one component pair for the 2-MMA scheme: hi[] = TF32 fragment, x[] = bf16 cross fragment.
+//   v0/v1 = the lane's two rows (g, g+8) at its first k element, v2/v3 = the same rows at its second k element
+PDL_DEV void split_cross(float v0, float v1, float v2, float v3, uint32_t (&hi)[4], uint32_t (&x)[4]) {
+    hi[0] = tf32_rna(v0); hi[1] = tf32_rna(v1); hi[2] = tf32_rna(v2); hi[3] = tf32_rna(v3);
+    x[0] = pack_bf16(v0 - u2f(hi[0]), v2 - u2f(hi[2]));
+    x[1] = pack_bf16(v1 - u2f(hi[1]), v3 - u2f(hi[3]));
+    x[2] = pack_bf16(v0, v2);
+    x[3] = pack_bf16(v1, v3);
+}
+// D(16x8) += A(16x16) * B(16x8), bf16 inputs, FP32 accumulate (mma.sync.m16n8k16).  lane = 4g + t:
+//   A: a0 (g; k = 2t, 2t+1)  a1 (g+8; 2t, 2t+1)  a2 (g; 2t+8, 2t+9)  a3 (g+8; 2t+8, 2t+9);  B: b0 (k = 2t, 2t+1; n = g)  b1 (k = 2t+8, 2t+9; n = g)
+PDL_DEV void warp_mma_bf16(float (&d)[PDL_NL][4], const uint32_t (&a)[PDL_NL][4], const uint32_t (&b)[PDL_NL][2]) {
+#ifdef PDL_EMULATE
+    float A[16][16], B[16][8];
+    for (int l = 0; l < 32; ++l) {
+        const int g = l >> 2, t = l & 3;
+        for (int e = 0; e < 2; ++e) {
+            const int sh = 16 * e;
+            A[g][2 * t + e] = u2f(((a[l][0] >> sh) & 0xFFFFu) << 16); A[g + 8][2 * t + e] = u2f(((a[l][1] >> sh) & 0xFFFFu) << 16);
+            A[g][2 * t + 8 + e] = u2f(((a[l][2] >> sh) & 0xFFFFu) << 16); A[g + 8][2 * t + 8 + e] = u2f(((a[l][3] >> sh) & 0xFFFFu) << 16);
+            B[2 * t + e][g] = u2f(((b[l][0] >> sh) & 0xFFFFu) << 16); B[2 * t + 8 + e][g] = u2f(((b[l][1] >> sh) & 0xFFFFu) << 16);
+        }
+    }
+    for (int l = 0; l < 32; ++l) {
+        const int g = l >> 2, t = l & 3;
+        for (int q = 0; q < 4; ++q) {
+            const int r = g + ((q & 2) ? 8 : 0), c = 2 * t + (q & 1);
+            float s = d[l][q];
+            for (int k = 0; k < 16; ++k) s += A[r][k] * B[k][c];
+            d[l][q] = s;
+        }
+    }
+#else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0][0]), "+f"(d[0][1]), "+f"(d[0][2]), "+f"(d[0][3])
+                 : "r"(a[0][0]), "r"(a[0][1]), "r"(a[0][2]), "r"(a[0][3]), "r"(b[0][0]), "r"(b[0][1]));
+#endif
+}
 PDL_DEV void warp_mma(float (&d)[PDL_NL][4], const uint32_t (&a)[PDL_NL][4], const uint32_t (&b)[PDL_NL][2]) {
 #ifdef PDL_EMULATE
     float A[16][8], B[8][8];
@@ -395,11 +457,20 @@ PDL_DEV void stage_thread2(const Params& P, float* sm, int tid) {
             const float w = W[e];
             const uint32_t uh = tf32_rna(w), ul = tf32_rna(w - u2f(uh));   // staged once per CTA: round the low part too
             base[HH_WHI + n * SF + k] = u2f(uh);
-            base[HH_WLO + n * SF + k] = u2f(ul);
-            if (DGRAD_T) {
-                base[HH_THI + k * SF + n] = u2f(uh);
-                base[HH_TLO + k * SF + n] = u2f(ul);
-            } else if (!DGRAD_MMA) {
+            if (!XBF_F) base[HH_WLO + n * SF + k] = u2f(ul);
+            else if ((k & 1) == 0) {                                       // packed bf16 cross operands of the pair (k, k+1)
+                const float w1 = (k + 1 < win) ? W[e + 1] : 0.f;
+                base[HH_WLO + n * SF + k] = u2f(pack_bf16(w, w1));
+                base[HH_WLO + n * SF + k + 1] = u2f(pack_bf16(w - u2f(uh), w1 - u2f(tf32_rna(w1))));
+            }
+            if (DGRAD_T) base[HH_THI + k * SF + n] = u2f(uh);
+            if (DGRAD_T && !XBF_D) base[HH_TLO + k * SF + n] = u2f(ul);
+            if (DGRAD_MMA && XBF_D && (n & 1) == 0) {                        // transposed cross plane: pairs along n
+                const float w1 = (n + 1 < wout) ? W[e + win] : 0.f;
+                base[HH_TLO + k * SF + n] = u2f(pack_bf16(w, w1));
+                base[HH_TLO + k * SF + n + 1] = u2f(pack_bf16(w - u2f(uh), w1 - u2f(tf32_rna(w1))));
+            }
+            if (!DGRAD_MMA) {
                 // FP32-pipe dgrad copy grouped by the lane column that owns input neuron k: t = (k%8)/2, i = 2*(k/8) + k%2
                 base[HH_WD + n * SD + ((k & 7) >> 1) * GS + 2 * (k >> 3) + (k & 1)] = w;
             }
@@ -489,14 +560,16 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
 #pragma unroll
                 for (int q = 0; q < NT8; ++q) {
 #pragma unroll
-                    for (int m = 0; m < NM; ++m) { accf[q][m][PDL_L][0] = 0.f; accf[q][m][PDL_L][1] = 0.f; accf[q][m][PDL_L][2] = 0.f; accf[q][m][PDL_L][3] = 0.f; }
+                    for (int m = 0; m < NM; ++m) {
+                        accf[q][m][PDL_L][0] = 0.f; accf[q][m][PDL_L][1] = 0.f; accf[q][m][PDL_L][2] = 0.f; accf[q][m][PDL_L][3] = 0.f;
+                    }
                     accf[q][0][PDL_L][0] = bl[8 * q + 2 * t];            // bias enters component 0 only
                     accf[q][0][PDL_L][1] = bl[8 * q + 2 * t + 1];
                 }
             }
 #pragma unroll
             for (int s = 0; s < NT8; ++s) {
-                uint32_t ahi[NM][PDL_NL][4], alo[NM][PDL_NL][4];
+                uint32_t ahi[NM][PDL_NL][4], alo[NM][PDL_NL][4];        // alo = the bf16 cross fragment when XBF_F
                 PDL_FOR_LANES {
 #pragma unroll
                     for (int m = 0; m < NM; ++m) {
@@ -504,10 +577,13 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                         const float v0 = h[PDL_L][2 * s][2 * m], v2 = h[PDL_L][2 * s + 1][2 * m];
                         const float v1 = (2 * m + 1 < J) ? h[PDL_L][2 * s][(2 * m + 1 < J) ? 2 * m + 1 : 0] : 0.f;
                         const float v3 = (2 * m + 1 < J) ? h[PDL_L][2 * s + 1][(2 * m + 1 < J) ? 2 * m + 1 : 0] : 0.f;
-                        split_tf32(v0, ahi[m][PDL_L][0], alo[m][PDL_L][0]);
-                        split_tf32(v1, ahi[m][PDL_L][1], alo[m][PDL_L][1]);
-                        split_tf32(v2, ahi[m][PDL_L][2], alo[m][PDL_L][2]);
-                        split_tf32(v3, ahi[m][PDL_L][3], alo[m][PDL_L][3]);
+                        if (XBF_F) split_cross(v0, v1, v2, v3, ahi[m][PDL_L], alo[m][PDL_L]);
+                        else {
+                            split_tf32(v0, ahi[m][PDL_L][0], alo[m][PDL_L][0]);
+                            split_tf32(v1, ahi[m][PDL_L][1], alo[m][PDL_L][1]);
+                            split_tf32(v2, ahi[m][PDL_L][2], alo[m][PDL_L][2]);
+                            split_tf32(v3, ahi[m][PDL_L][3], alo[m][PDL_L][3]);
+                        }
                     }
                 }
 #pragma unroll
@@ -519,11 +595,18 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                         const pdl_f2 vl = ld2(Wlo + (8 * q + g) * SF + 8 * s + 2 * t);
                         bhi[PDL_L][0] = f2u(vh.x); bhi[PDL_L][1] = f2u(vh.y); blo[PDL_L][0] = f2u(vl.x); blo[PDL_L][1] = f2u(vl.y);
                     }
+                    if (XBF_F) {
 #pragma unroll
-                    for (int m = 0; m < NM; ++m) {
-                        warp_mma(accf[q][m], alo[m], bhi);
-                        warp_mma(accf[q][m], ahi[m], blo);
-                        warp_mma(accf[q][m], ahi[m], bhi);
+                        for (int m = 0; m < NM; ++m) warp_mma(accf[q][m], ahi[m], bhi);
+#pragma unroll
+                        for (int m = 0; m < NM; ++m) warp_mma_bf16(accf[q][m], alo[m], blo);
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < NM; ++m) {
+                            warp_mma(accf[q][m], alo[m], bhi);
+                            warp_mma(accf[q][m], ahi[m], blo);
+                            warp_mma(accf[q][m], ahi[m], bhi);
+                        }
                     }
                 }
             }
@@ -754,8 +837,11 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                         }
 #pragma unroll
                         for (int c = 0; c < J; ++c) {
+                            if (XBF_W) split_cross(v[0][c], v[1][c], v[2][c], v[3][c], ahi[c][PDL_L], alo[c][PDL_L]);
+                            else {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) split_tf32_raw(v[q][c], ahi[c][PDL_L][q], alo[c][PDL_L][q]);
+                                for (int q = 0; q < 4; ++q) split_tf32_raw(v[q][c], ahi[c][PDL_L][q], alo[c][PDL_L][q]);
+                            }
                         }
                         bs[PDL_L][0] = v[0][0] + v[2][0];                 // bias gradient: sum over points of component 0
                         bs[PDL_L][1] = v[1][0] + v[3][0];
@@ -764,9 +850,11 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                     PDL_FOR_LANES { if ((lane & 3) == mt) { bsel[PDL_L][0] = bs[PDL_L][0]; bsel[PDL_L][1] = bs[PDL_L][1]; } }
 #pragma unroll
                     for (int nt0 = 0; nt0 < NT8; nt0 += NTB) {
-                        // NTB n8 tiles at a time, three accumulators each (lo*hi, hi*lo, hi*hi): 3*NTB independent MMA chains of length J
+                        // NTB n8 tiles at a time, one accumulator per MMA kind (lo*hi, hi*lo, hi*hi -- or hi*hi and the bf16 cross MMA):
+                        // NACW*NTB independent MMA chains of length J
+                        constexpr int NACW = XBF_W ? 2 : 3;
                         uint32_t bhi[NTB][J][PDL_NL][2], blo[NTB][J][PDL_NL][2];
-                        float c4[NTB][3][PDL_NL][4];
+                        float c4[NTB][NACW][PDL_NL][4];
                         PDL_FOR_LANES {
                             const int g = lane >> 2, t = lane & 3;
 #pragma unroll
@@ -778,12 +866,19 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                                     load_entry(bufH + (2 * t + 1) * SA + k * JA, bufH + 8 * SA + (2 * t + 1) * SB + k * JB, w1);
 #pragma unroll
                                     for (int c = 0; c < J; ++c) {
-                                        split_tf32_raw(w0[c], bhi[b][c][PDL_L][0], blo[b][c][PDL_L][0]);
-                                        split_tf32_raw(w1[c], bhi[b][c][PDL_L][1], blo[b][c][PDL_L][1]);
+                                        if (XBF_W) {                          // k slots 2t, 2t+1 = points 2t, 2t+1
+                                            const uint32_t h0 = tf32_rna(w0[c]), h1 = tf32_rna(w1[c]);
+                                            bhi[b][c][PDL_L][0] = h0; bhi[b][c][PDL_L][1] = h1;
+                                            blo[b][c][PDL_L][0] = pack_bf16(w0[c], w1[c]);
+                                            blo[b][c][PDL_L][1] = pack_bf16(w0[c] - u2f(h0), w1[c] - u2f(h1));
+                                        } else {
+                                            split_tf32_raw(w0[c], bhi[b][c][PDL_L][0], blo[b][c][PDL_L][0]);
+                                            split_tf32_raw(w1[c], bhi[b][c][PDL_L][1], blo[b][c][PDL_L][1]);
+                                        }
                                     }
                                 }
 #pragma unroll
-                                for (int q = 0; q < 3; ++q) { c4[b][q][PDL_L][0] = 0.f; c4[b][q][PDL_L][1] = 0.f; c4[b][q][PDL_L][2] = 0.f; c4[b][q][PDL_L][3] = 0.f; }
+                                for (int q = 0; q < NACW; ++q) { c4[b][q][PDL_L][0] = 0.f; c4[b][q][PDL_L][1] = 0.f; c4[b][q][PDL_L][2] = 0.f; c4[b][q][PDL_L][3] = 0.f; }
                             }
                         }
 #pragma unroll
@@ -791,9 +886,14 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
 #pragma unroll
                             for (int b = 0; b < NTB; ++b) {
                                 if (nt0 + b < NT8) {
-                                    warp_mma(c4[b][0], alo[c], bhi[b][c]);
-                                    warp_mma(c4[b][1], ahi[c], blo[b][c]);
-                                    warp_mma(c4[b][2], ahi[c], bhi[b][c]);
+                                    if (XBF_W) {
+                                        warp_mma(c4[b][0], ahi[c], bhi[b][c]);
+                                        warp_mma_bf16(c4[b][1], alo[c], blo[b][c]);
+                                    } else {
+                                        warp_mma(c4[b][0], alo[c], bhi[b][c]);
+                                        warp_mma(c4[b][1], ahi[c], blo[b][c]);
+                                        warp_mma(c4[b][NACW - 1], ahi[c], bhi[b][c]);
+                                    }
                                 }
                             }
                         }
@@ -803,10 +903,17 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                                 if (nt0 + b < NT8) {
                                     float* q = wpl + ((mt * NT8 + nt0 + b) * 32 + lane) * 4;
                                     pdl_f4 r;
-                                    r.x = (c4[b][0][PDL_L][0] + c4[b][1][PDL_L][0]) + c4[b][2][PDL_L][0];
-                                    r.y = (c4[b][0][PDL_L][1] + c4[b][1][PDL_L][1]) + c4[b][2][PDL_L][1];
-                                    r.z = (c4[b][0][PDL_L][2] + c4[b][1][PDL_L][2]) + c4[b][2][PDL_L][2];
-                                    r.w = (c4[b][0][PDL_L][3] + c4[b][1][PDL_L][3]) + c4[b][2][PDL_L][3];
+                                    if (XBF_W) {
+                                        r.x = c4[b][0][PDL_L][0] + c4[b][1][PDL_L][0];
+                                        r.y = c4[b][0][PDL_L][1] + c4[b][1][PDL_L][1];
+                                        r.z = c4[b][0][PDL_L][2] + c4[b][1][PDL_L][2];
+                                        r.w = c4[b][0][PDL_L][3] + c4[b][1][PDL_L][3];
+                                    } else {
+                                        r.x = (c4[b][0][PDL_L][0] + c4[b][1][PDL_L][0]) + c4[b][NACW - 1][PDL_L][0];
+                                        r.y = (c4[b][0][PDL_L][1] + c4[b][1][PDL_L][1]) + c4[b][NACW - 1][PDL_L][1];
+                                        r.z = (c4[b][0][PDL_L][2] + c4[b][1][PDL_L][2]) + c4[b][NACW - 1][PDL_L][2];
+                                        r.w = (c4[b][0][PDL_L][3] + c4[b][1][PDL_L][3]) + c4[b][NACW - 1][PDL_L][3];
+                                    }
                                     if (!first) { const pdl_f4 o = ldg4(q); r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
                                     stg4(q, r);
                                 }
@@ -832,7 +939,9 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
 #pragma unroll
                     for (int q = 0; q < NT8; ++q) {
 #pragma unroll
-                        for (int m = 0; m < NM; ++m) { hbfr[q][m][PDL_L][0] = 0.f; hbfr[q][m][PDL_L][1] = 0.f; hbfr[q][m][PDL_L][2] = 0.f; hbfr[q][m][PDL_L][3] = 0.f; }
+                        for (int m = 0; m < NM; ++m) {
+                            hbfr[q][m][PDL_L][0] = 0.f; hbfr[q][m][PDL_L][1] = 0.f; hbfr[q][m][PDL_L][2] = 0.f; hbfr[q][m][PDL_L][3] = 0.f;
+                        }
                     }
                 }
 #pragma unroll
@@ -844,10 +953,13 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                             const float v0 = zbk[PDL_L][2 * s][2 * m], v2 = zbk[PDL_L][2 * s + 1][2 * m];
                             const float v1 = (2 * m + 1 < J) ? zbk[PDL_L][2 * s][(2 * m + 1 < J) ? 2 * m + 1 : 0] : 0.f;
                             const float v3 = (2 * m + 1 < J) ? zbk[PDL_L][2 * s + 1][(2 * m + 1 < J) ? 2 * m + 1 : 0] : 0.f;
-                            split_tf32_dg(v0, ahi[m][PDL_L][0], alo[m][PDL_L][0]);
-                            split_tf32_dg(v1, ahi[m][PDL_L][1], alo[m][PDL_L][1]);
-                            split_tf32_dg(v2, ahi[m][PDL_L][2], alo[m][PDL_L][2]);
-                            split_tf32_dg(v3, ahi[m][PDL_L][3], alo[m][PDL_L][3]);
+                            if (XBF_D) split_cross(v0, v1, v2, v3, ahi[m][PDL_L], alo[m][PDL_L]);
+                            else {
+                                split_tf32_dg(v0, ahi[m][PDL_L][0], alo[m][PDL_L][0]);
+                                split_tf32_dg(v1, ahi[m][PDL_L][1], alo[m][PDL_L][1]);
+                                split_tf32_dg(v2, ahi[m][PDL_L][2], alo[m][PDL_L][2]);
+                                split_tf32_dg(v3, ahi[m][PDL_L][3], alo[m][PDL_L][3]);
+                            }
                         }
                     }
 #pragma unroll
@@ -857,19 +969,29 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                             const int g = lane >> 2, t = lane & 3;
                             if (DGRAD_T) {
                                 const pdl_f2 vh = ld2(Thi + (8 * q + g) * SF + 8 * s + 2 * t);
-                                const pdl_f2 vl = ld2(Tlo + (8 * q + g) * SF + 8 * s + 2 * t);
-                                bhi[PDL_L][0] = f2u(vh.x); bhi[PDL_L][1] = f2u(vh.y); blo[PDL_L][0] = f2u(vl.x); blo[PDL_L][1] = f2u(vl.y);
+                                bhi[PDL_L][0] = f2u(vh.x); bhi[PDL_L][1] = f2u(vh.y);
                             } else {                            // B[n][k] = W[n][k] straight from the forward copies
                                 const int o = (8 * s + 2 * t) * SF + 8 * q + g;
                                 bhi[PDL_L][0] = f2u(Whi_[o]); bhi[PDL_L][1] = f2u(Whi_[o + SF]);
-                                blo[PDL_L][0] = f2u(Wlo_[o]); blo[PDL_L][1] = f2u(Wlo_[o + SF]);
+                                if (!XBF_D) { blo[PDL_L][0] = f2u(Wlo_[o]); blo[PDL_L][1] = f2u(Wlo_[o + SF]); }
+                            }
+                            if (DGRAD_T || XBF_D) {               // lo plane of W^T, or its packed bf16 cross plane (the only transposed plane in mode 2)
+                                const pdl_f2 vl = ld2(Tlo + (8 * q + g) * SF + 8 * s + 2 * t);
+                                blo[PDL_L][0] = f2u(vl.x); blo[PDL_L][1] = f2u(vl.y);
                             }
                         }
+                        if (XBF_D) {
 #pragma unroll
-                        for (int m = 0; m < NM; ++m) {
-                            warp_mma(hbfr[q][m], alo[m], bhi);
-                            warp_mma(hbfr[q][m], ahi[m], blo);
-                            warp_mma(hbfr[q][m], ahi[m], bhi);
+                            for (int m = 0; m < NM; ++m) warp_mma(hbfr[q][m], ahi[m], bhi);
+#pragma unroll
+                            for (int m = 0; m < NM; ++m) warp_mma_bf16(hbfr[q][m], alo[m], blo);
+                        } else {
+#pragma unroll
+                            for (int m = 0; m < NM; ++m) {
+                                warp_mma(hbfr[q][m], alo[m], bhi);
+                                warp_mma(hbfr[q][m], ahi[m], blo);
+                                warp_mma(hbfr[q][m], ahi[m], bhi);
+                            }
                         }
                     }
                 }

@@ -134,7 +134,10 @@ int smem_floats(const PlanMeta& m, int nw) {
         const int SO_XI = WP * D + WP + WP + 1 + 7 * H;
         const int SACC = (SO_XI + KX * TP + 3) / 4 * 4;
         const int SM_HH = (WP * D + WP + 3) / 4 * 4;
-        const int HH_B = (m.dgrad_mma == 1) ? 4 * WP * SF : (m.dgrad_mma ? 2 * WP * SF : (2 * WP * SF + WP * SD));
+        // weight planes per hidden->hidden layer: W hi + W lo (or the packed bf16 cross plane), then W^T hi + lo/cross (mode 1), or only
+        // the W^T cross plane (mode 2 with bf16 cross terms), or the FP32-pipe dgrad copy
+        const int HH_B = (m.dgrad_mma == 1) ? 4 * WP * SF
+                       : (m.dgrad_mma ? (((m.cross_bf16 & 2) ? 3 : 2) * WP * SF) : (2 * WP * SF + WP * SD));
         const int HH_SIZE = (HH_B + WP + 3) / 4 * 4;
         const int SM_WH = SM_HH + NHH * HH_SIZE;
         const int SM_RAT = (SM_WH + WP + 1 + 3) / 4 * 4;
@@ -241,6 +244,15 @@ std::string generate_plan_source(const PlanSpec& spec, PlanMeta* meta_out) {
         // weight gradient on the tensor pipe: measured faster everywhere except Rational nets that also run the data gradient there
         // (register pressure; heat 5.44 -> 5.81 ms, burgers 7.08 -> 7.74 ms), see experiments/README.md
         meta.wgrad_mma = (spec.wgrad_mma >= 0) ? (spec.wgrad_mma ? 1 : 0) : ((spec.activation == 1 && meta.dgrad_mma) ? 0 : 1);
+        // cross terms hi*lo + lo*hi of the split products as ONE bf16 m16n8k16 MMA (2 tensor-pipe instructions per product instead of
+        // 3); bit mask: 1 = forward, 2 = data gradient, 4 = weight gradient.  Default 6: measured 8-11 % faster with unchanged parity
+        // errors; the forward (bit 1) would gain another 3-7 % but its errors reach 1.4e-5 on the derivative features (gate: 1e-5).
+        meta.cross_bf16 = (spec.cross_bf16 >= 0) ? (spec.cross_bf16 & 7) : 6;
+        if (!meta.dgrad_mma) meta.cross_bf16 &= ~2;
+        if (!meta.wgrad_mma) meta.cross_bf16 &= ~4;
+        // mode 2 reads the TF32 lo plane of W that the bf16 forward replaces: forward bf16 then needs the data gradient bf16 as well
+        if (meta.dgrad_mma == 2 && (meta.cross_bf16 & 1)) meta.cross_bf16 |= 2;
+        if (meta.dgrad_mma == 2 && (meta.cross_bf16 & 2) && smem_floats(meta, nw) * 4 > 227 * 1024) meta.cross_bf16 &= ~3;
     }
     while (nw > 1 && smem_floats(meta, nw) * 4 > 227 * 1024) --nw;
     if (smem_floats(meta, nw) * 4 > 227 * 1024) throw std::runtime_error("plan does not fit in shared memory");
@@ -256,7 +268,7 @@ std::string generate_plan_source(const PlanSpec& spec, PlanMeta* meta_out) {
       << "\n#define PDL_K " << K << "\n#define PDL_ACT " << spec.activation << "\n#define PDL_NS " << NS
       << "\n#define PDL_NW " << nw << "\n#define PDL_MODE " << spec.mode << "\n#define PDL_SF " << meta.sf
       << "\n#define PDL_GS " << meta.gs << "\n#define PDL_DGRAD_MMA " << meta.dgrad_mma
-      << "\n#define PDL_WGRAD_MMA " << meta.wgrad_mma << "\n";
+      << "\n#define PDL_WGRAD_MMA " << meta.wgrad_mma << "\n#define PDL_CROSS_BF16 " << meta.cross_bf16 << "\n";
     o << "#ifdef PDL_EMULATE\n#define PDL_GEN static inline\n#else\n#define PDL_GEN __host__ __device__ __forceinline__\n#endif\n";
 
     // widths / first-order component -> axis

@@ -123,6 +123,33 @@ def test_emulated_engines_explicitly(name, engine, dgrad, wgrad, monkeypatch):
     assert rel_max(out["grad_xi"], og[-1].numpy()) <= TOL
 
 
+@pytest.mark.parametrize("name,dgrad,wgrad,cross,tol", [
+    ("heat_tanh", "1", "1", "0", TOL), ("ks_tanh", "2", "1", "0", TOL),                  # plain 3xTF32 everywhere
+    ("heat_tanh", "1", "1", "6", TOL), ("ks_tanh", "2", "1", "6", TOL), ("kdv_tanh", "1", "1", "6", TOL),   # the default, spelled out
+    ("burgers_rational20", "1", "0", "2", TOL), ("heat3d_tanh", "0", "1", "4", TOL), ("rd2d_tanh", "2", "1", "6", TOL),
+    ("heat_tanh", "1", "1", "7", 3e-5), ("ks_rational", "2", "1", "7", 3e-5)])           # bf16 forward too: opt-in, misses the 1e-5 gate
+def test_emulated_bf16_cross_term_variants(name, dgrad, wgrad, cross, tol, monkeypatch):
+    """PDL_CROSS_BF16 bit mask (1 forward, 2 data gradient, 4 weight gradient): the cross terms hi*lo + lo*hi of a split product as
+    one bf16 mma.sync.m16n8k16 (modelled lane-exactly) next to the TF32 hi*hi MMA.  Default = 6; the forward bit is opt-in because
+    its error on the derivative features reaches 1.4e-5 (measured on the B200 and reproduced by the emulation)."""
+    monkeypatch.setenv("PDL_ENGINE", "mma")
+    monkeypatch.setenv("PDL_DGRAD_MMA", dgrad)
+    monkeypatch.setenv("PDL_WGRAD_MMA", wgrad)
+    monkeypatch.setenv("PDL_CROSS_BF16", cross)
+    g = GoldenCase(name)
+    desc, keep = desc_for(g)
+    want_mask = int(cross) & ~(0 if dgrad != "0" else 2) & ~(0 if wgrad != "0" else 4)
+    if dgrad == "2" and (want_mask & 1):
+        want_mask |= 2
+    assert "#define PDL_CROSS_BF16 %d\n" % want_mask in L.plan_source(desc)
+    out = emu.run_emu(desc, g.points.numpy(), [p.numpy() for p in g.params], g.xi.numpy(), np.array(g.mask, dtype=np.uint8), n_ctas=2)
+    want = float(g.z["coll_loss"])
+    assert abs(out["loss"] - want) <= tol * want
+    assert rel_max(out["residual"], g.z["residual"]) <= tol
+    assert rel_max(out["grad_params"], np.concatenate([x.numpy().ravel() for x in g.grads])) <= tol
+    assert rel_max(out["grad_xi"], g.z["grad_xi"]) <= tol
+
+
 @pytest.mark.parametrize("name", ["heat_tanh", "ks_rational"])
 def test_emulated_device_row_count(name):
     """The row count read from memory (pdl_launch_args.n_points_dev, captured epochs): a launch over the whole buffer with the count
