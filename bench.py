@@ -307,21 +307,29 @@ def run_ours(args):
                 "flops_per_point": plan.flops_per_point, "points_per_launch": B, "kernel_ms": k_ms,
                 "hbm_gbs_algorithmic": hbm_bytes / (k_ms * 1e-3) / 1e9,
                 "hbm_peak_gbs": peaks.get("hbm_gbs"), "traffic": traffic}
-    # the tensor-pipe view of the same launch: executed (3xTF32, padded) MMA flops against the measured mma.sync TF32 rate
+    # the tensor-pipe view of the same launch: executed MMA instructions (split products, padding included) against the measured
+    # mma.sync rate.  A TF32 m16n8k8 and a bf16 m16n8k16 occupy the pipe equally long (277 vs 554 TFLOP/s measured), so the unit
+    # is the TF32-equivalent instruction: 2048 flop.
     try:
         import re
         src = L.plan_source(plan.desc)
-        df = {k: int(v) for k, v in re.findall(r"#define (PDL_WP|PDL_J|PDL_H|PDL_DGRAD_MMA|PDL_WGRAD_MMA) (\d+)", src)}
+        df = {k: int(v) for k, v in re.findall(r"#define (PDL_WP|PDL_J|PDL_H|PDL_DGRAD_MMA|PDL_WGRAD_MMA|PDL_CROSS_BF16) (\d+)", src)}
         if "jet_mlp_kernel_mma.cuh" in src:
             nt8, nm, nmt = df["PDL_WP"] // 8, (df["PDL_J"] + 1) // 2, (df["PDL_WP"] + 15) // 16
-            per_layer = 3 * nt8 * nt8 * nm * (1 + df["PDL_DGRAD_MMA"]) + 3 * nmt * nt8 * df["PDL_J"] * df["PDL_WGRAD_MMA"]
+            xb = df.get("PDL_CROSS_BF16", 0)
+            per_prod = {"forward": 2 if xb & 1 else 3, "dgrad": 2 if xb & 2 else 3, "wgrad": 2 if xb & 4 else 3}
+            per_layer = (per_prod["forward"] * nt8 * nt8 * nm + (per_prod["dgrad"] * nt8 * nt8 * nm if df["PDL_DGRAD_MMA"] else 0) +
+                         (per_prod["wgrad"] * nmt * nt8 * df["PDL_J"] if df["PDL_WGRAD_MMA"] else 0))
             mma_flops_pt = per_layer * (df["PDL_H"] - 1) * (16 * 8 * 8 * 2) / 8.0
             exe = mma_flops_pt * B / (k_ms * 1e-3) / 1e12
             roofline["tensor_pipe"] = {"executed_tflops": exe, "peak": 277.0, "frac": exe / 277.0, "mma_per_tile_layer": per_layer,
+                                       "mma_per_product": per_prod,
                                        "contractions_on_tensor_pipe": ["forward"] + (["dgrad"] if df["PDL_DGRAD_MMA"] else []) +
                                                                       (["wgrad"] if df["PDL_WGRAD_MMA"] else []),
-                                       "peak_source": "mma.sync.m16n8k8 TF32 microbenchmark, profiles/r01_ubench.txt (277 TFLOP/s); "
-                                                      "3 MMAs per product (hi/lo split) and padding are executed, not algorithmic, flops"}
+                                       "peak_source": "mma.sync.m16n8k8 TF32 microbenchmark, profiles/r01_ubench.txt (277 TFLOP/s = "
+                                                      "1.35e11 MMA instructions/s; bf16 m16n8k16 issues at the same rate); split "
+                                                      "products (3 MMAs, or TF32 hi*hi + one bf16 cross-term MMA) and padding are "
+                                                      "executed, not algorithmic, work; executed_tflops counts 2048 flop per MMA"}
     except Exception as ex:                                                  # informational only
         roofline["tensor_pipe"] = {"error": str(ex)}
 

@@ -199,6 +199,17 @@ PDL_DEV void xor_add(float (&v)[PDL_NL][N], int m) {
 // ---------------------------------------------------------------------------------------------
 // activation sigmas: s[m] = sigma^(m)(z0), m = 0..NS-1
 // ---------------------------------------------------------------------------------------------
+// reciprocal of the Rational denominator: MUFU.RCP (1 ulp for normal inputs) instead of the ~9-instruction IEEE division with its
+// slow-path branch; see jet_mlp_kernel_mma.cuh
+PDL_DEV float rcp_fast(float d) {
+#if defined(PDL_EMULATE) || defined(PDL_RCP_IEEE)
+    return 1.0f / d;
+#else
+    float r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(d));
+    return r;
+#endif
+}
 PDL_DEV float rat_fact(int k) { float f = 1.f; for (int i = 2; i <= k; ++i) f *= (float)i; return f; }
 
 PDL_DEV void sigmas(float z0, const float* rp, float (&s)[NS], float (&r)[NS], float& inv_d0) {
@@ -214,7 +225,7 @@ PDL_DEV void sigmas(float z0, const float* rp, float (&s)[NS], float (&r)[NS], f
     nk[2] = a2 + 3.f * a3 * z0;
     nk[3] = a3;
     const float d0 = b0 + z0 * (b1 + b2 * z0), d1 = b1 + 2.f * b2 * z0, d2 = b2;
-    inv_d0 = 1.0f / d0;
+    inv_d0 = rcp_fast(d0);
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
         float t = (k < 4) ? nk[k < 4 ? k : 0] : 0.f;

@@ -70,6 +70,12 @@ constexpr int NFRAG = NMT * NT8;            // C fragments of one layer's weight
 #define PDL_WGRAD_ROLL_MT (PDL_J >= 5)      // measured: from J = 5 on the unrolled m-tile loop costs more in instruction fetch than it gains
 #endif
 constexpr int NTB = PDL_WGRAD_NTB;          // n8 tiles per weight-gradient step (independent MMA chains vs registers)
+#ifndef PDL_ADJ_FUSED
+#define PDL_ADJ_FUSED 1
+#endif
+// order of the hidden-layer adjoint: 1 = one activation pass per layer shared by the recomputed forward and the adjoint (one tanh /
+// Rational recurrence less per neuron and layer), 0 = the classic order (adjoint of layer l and recompute of layer l-1 in one loop)
+constexpr bool ADJ_FUSED = (PDL_ADJ_FUSED != 0);
 constexpr int GS = PDL_GS;                  // group stride of the dgrad weight copy  Wd[n][g4][i]
 constexpr int SD = 4 * GS;
 constexpr int NHH = (H > 1) ? (H - 1) : 0;  // hidden->hidden linear layers
@@ -347,6 +353,18 @@ PDL_DEV int own_neuron(int t, int i) { return 8 * (i >> 1) + 2 * t + (i & 1); }
 // ---------------------------------------------------------------------------------------------
 // activation sigmas: s[m] = sigma^(m)(z0), m = 0..NS-1
 // ---------------------------------------------------------------------------------------------
+// reciprocal of the Rational denominator.  1.0f / d compiles to MUFU.RCP + two Newton steps + a branch to a slow path for
+// subnormals: ~9 instructions and a basic-block split per evaluation, three evaluations per neuron and layer.  MUFU.RCP alone is
+// within 1 ulp for normal d (the denominator b0 + b1 z + b2 z^2 is O(1) wherever the activation is usable at all).
+PDL_DEV float rcp_fast(float d) {
+#if defined(PDL_EMULATE) || defined(PDL_RCP_IEEE)
+    return 1.0f / d;
+#else
+    float r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(d));
+    return r;
+#endif
+}
 PDL_DEV float rat_fact(int k) { float f = 1.f; for (int i = 2; i <= k; ++i) f *= (float)i; return f; }
 
 PDL_DEV void sigmas(float z0, const float* rp, float (&s)[NS], float (&r)[NS], float& inv_d0) {
@@ -362,7 +380,7 @@ PDL_DEV void sigmas(float z0, const float* rp, float (&s)[NS], float (&r)[NS], f
     nk[2] = a2 + 3.f * a3 * z0;
     nk[3] = a3;
     const float d0 = b0 + z0 * (b1 + b2 * z0), d1 = b1 + 2.f * b2 * z0, d2 = b2;
-    inv_d0 = 1.0f / d0;
+    inv_d0 = rcp_fast(d0);
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
         float t = (k < 4) ? nk[k < 4 ? k : 0] : 0.f;
@@ -414,6 +432,24 @@ PDL_DEV void act_forward(const float (&z)[J], const float* rp, float (&h)[J]) {
 PDL_DEV void act_adjoint(const float (&z)[J], const float (&hb)[J], const float* rp, float (&zb)[J], float (&ga)[7]) {
     float s[NS], r[NS], inv, sb[NS - 1];
     sigmas(z[0], rp, s, r, inv);
+    pdl_act_adj(z, hb, s, zb, sb);
+    float z0b = 0.f;
+#pragma unroll
+    for (int m = 0; m < NS - 1; ++m) z0b += sb[m] * s[m + 1];
+    zb[0] = z0b;
+#if PDL_ACT == 1
+    rational_param_adjoint(z[0], rp, r, inv, sb, ga);
+#else
+    (void)ga;
+#endif
+}
+
+// both at once for one neuron of the layer below: h = act(z) (forward, recomputed) and zb = act'(z, hb) (adjoint), sharing the
+// activation derivatives s[] -- the tanh / the Rational recurrence is evaluated once
+PDL_DEV void act_forward_adjoint(const float (&z)[J], const float (&hb)[J], const float* rp, float (&h)[J], float (&zb)[J], float (&ga)[7]) {
+    float s[NS], r[NS], inv, sb[NS - 1];
+    sigmas(z[0], rp, s, r, inv);
+    pdl_act_fwd(z, s, h);
     pdl_act_adj(z, hb, s, zb, sb);
     float z0b = 0.f;
 #pragma unroll
@@ -703,38 +739,11 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
             }
         }
         // ---------------- hidden -> hidden layers, adjoint ----------------
-        for (int l = H - 1; l >= 1; --l) {
-            float ga[PDL_NL][7];
-            float zbk[PDL_NL][NPL][J];            // adjoint of the pre-activations kept for the tensor-pipe data gradient
-            PDL_FOR_LANES {
-                const int pg = lane >> 2, g4 = lane & 3;
-#pragma unroll
-                for (int q = 0; q < 7; ++q) ga[PDL_L][q] = 0.f;
-#pragma unroll
-                for (int i = 0; i < NPL; ++i) {
-                    const int n = own_neuron(g4, i);
-                    float z[J], zb[J];
-                    scratch_load(zs, l - 1, i, lane, z);
-                    act_adjoint(z, hb[PDL_L][i], sm + SM_RAT + l * 8, zb, ga[PDL_L]);
-                    store_entry(bufZ + pg * SA + n * JA, bufZ + 8 * SA + pg * SB + n * JB, zb);
-                    if (DGRAD_MMA) {
-#pragma unroll
-                        for (int c = 0; c < J; ++c) zbk[PDL_L][i][c] = zb[c];
-                    }
-                    // activations of the layer below (input of this linear layer), recomputed
-                    float zi[J], hi[J];
-                    if (l >= 2) scratch_load(zs, l - 2, i, lane, zi);
-                    else layer0_preact(sm, n, x[PDL_L], zi);
-                    act_forward(zi, sm + SM_RAT + (l - 1) * 8, hi);
-                    store_entry(bufH + pg * SA + n * JA, bufH + 8 * SA + pg * SB + n * JB, hi);
-                }
-            }
-            PDL_SYNCWARP();
-#if PDL_ACT == 1
-            xor_add<7>(ga, 1); xor_add<7>(ga, 2); xor_add<7>(ga, 4); xor_add<7>(ga, 8); xor_add<7>(ga, 16);
-            PDL_FOR_LANES { if (lane == 0) { for (int q = 0; q < 7; ++q) sacc[SO_RAT + l * 7 + q] += ga[PDL_L][q]; } }
-#endif
-            const float* Wd = sm + SM_HH + (l - 1) * HH_SIZE + HH_WD;
+        // Order per layer l (top down): data gradient of layer l (zb_l -> hb_{l-1}), then ONE pass over the lane's neurons of layer
+        // l-1 that evaluates the activation derivatives once and uses them twice -- h_{l-1} = act(z_{l-1}) (the weight gradient's
+        // other operand, recomputed instead of stored) and zb_{l-1} = act'(z_{l-1}, hb_{l-1}) in place -- then the weight gradient
+        // of layer l.  hb[] therefore holds hb_l or zb_l alternately; bufZ holds zb_l for the shared-memory consumers.
+        auto wgrad_layer = [&](const int l) {
             PDL_FOR_LANES {
                 const int pg = lane >> 2, g4 = lane & 3, g8 = lane >> 2;
                 // ---- weight gradient: Wbar[n][k] += sum_p sum_c zb[p][n][c] * h[p][k][c]   (n in g8 group, k in g4 group)
@@ -774,36 +783,6 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                         stg4(wpl + (a / 4 * 32 + lane) * 4, t);
                     }
                 }
-                // ---- data gradient on the FP32 pipe: hb[p][k] = sum_n zb[p][n] * W[n][k]   (k = the lane's own neurons)
-                if (!DGRAD_MMA) {
-#pragma unroll
-                for (int i = 0; i < NPL; ++i) {
-#pragma unroll
-                    for (int c = 0; c < J; ++c) hb[PDL_L][i][c] = 0.f;
-                }
-                const float* zA = bufZ + pg * SA;
-                const float* zB = bufZ + 8 * SA + pg * SB;
-#pragma unroll 2
-                for (int nc = 0; nc < WP; nc += 4) {
-                    float a[4][J];
-#pragma unroll
-                    for (int nn = 0; nn < 4; ++nn) load_entry(zA + (nc + nn) * JA, zB + (nc + nn) * JB, a[nn]);
-#pragma unroll
-                    for (int nn = 0; nn < 4; ++nn) {
-                        const float* wr = Wd + (nc + nn) * SD + g4 * GS;
-                        float w[NPL];
-#pragma unroll
-                        for (int i = 0; i + 3 < NPL; i += 4) { const pdl_f4 t = ld4(wr + i); w[i] = t.x; w[i + 1] = t.y; w[i + 2] = t.z; w[i + 3] = t.w; }
-                        if ((NPL & 3) >= 2) { const pdl_f2 t = ld2(wr + (NPL & ~3)); w[(NPL & ~3)] = t.x; w[(NPL & ~3) + 1 < NPL ? (NPL & ~3) + 1 : 0] = t.y; }
-                        if (NPL & 1) w[NPL - 1] = wr[NPL - 1];
-#pragma unroll
-                        for (int i = 0; i < NPL; ++i) {
-#pragma unroll
-                            for (int c = 0; c < J; ++c) hb[PDL_L][i][c] += a[nn][c] * w[i];
-                        }
-                    }
-                }
-                }
             }
             if (WGRAD_MMA) {
                 // ---- weight gradient on the tensor pipe.  Wbar[n][k] = sum_c sum_p zb[p][n][c] h[p][k][c]: M = n (m16 tiles), N = k
@@ -812,6 +791,28 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                 // accumulated from zero on the tensor pipe (which truncates) and added to the running FP32 partial sum with a
                 // rounded FADD, so the long sum over tiles keeps round-to-nearest behaviour.
                 float* wpl = wp + (l - 1) * WPRIV_LAYER;
+                uint32_t bhi[NTB][J][PDL_NL][2], blo[NTB][J][PDL_NL][2];
+                auto make_b = [&](const int slot, const int nt) {           // B fragments of n8 tile nt -> slot (blo = bf16 cross fragment when XBF_W)
+                    PDL_FOR_LANES {
+                        const int g = lane >> 2, t = lane & 3;
+                        const int k = 8 * nt + g;
+                        float w0[J], w1[J];
+                        load_entry(bufH + (2 * t) * SA + k * JA, bufH + 8 * SA + (2 * t) * SB + k * JB, w0);
+                        load_entry(bufH + (2 * t + 1) * SA + k * JA, bufH + 8 * SA + (2 * t + 1) * SB + k * JB, w1);
+#pragma unroll
+                        for (int c = 0; c < J; ++c) {
+                            if (XBF_W) {                          // k slots 2t, 2t+1 = points 2t, 2t+1
+                                const uint32_t h0 = tf32_rna(w0[c]), h1 = tf32_rna(w1[c]);
+                                bhi[slot][c][PDL_L][0] = h0; bhi[slot][c][PDL_L][1] = h1;
+                                blo[slot][c][PDL_L][0] = pack_bf16(w0[c], w1[c]);
+                                blo[slot][c][PDL_L][1] = pack_bf16(w0[c] - u2f(h0), w1[c] - u2f(h1));
+                            } else {
+                                split_tf32_raw(w0[c], bhi[slot][c][PDL_L][0], blo[slot][c][PDL_L][0]);
+                                split_tf32_raw(w1[c], bhi[slot][c][PDL_L][1], blo[slot][c][PDL_L][1]);
+                            }
+                        }
+                    }
+                };
                 float bsel[PDL_NL][2];
                 PDL_FOR_LANES { bsel[PDL_L][0] = 0.f; bsel[PDL_L][1] = 0.f; }
 #if PDL_WGRAD_ROLL_MT
@@ -853,30 +854,11 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                         // NTB n8 tiles at a time, one accumulator per MMA kind (lo*hi, hi*lo, hi*hi -- or hi*hi and the bf16 cross MMA):
                         // NACW*NTB independent MMA chains of length J
                         constexpr int NACW = XBF_W ? 2 : 3;
-                        uint32_t bhi[NTB][J][PDL_NL][2], blo[NTB][J][PDL_NL][2];
                         float c4[NTB][NACW][PDL_NL][4];
-                        PDL_FOR_LANES {
-                            const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-                            for (int b = 0; b < NTB; ++b) {
-                                if (nt0 + b < NT8) {
-                                    const int k = 8 * (nt0 + b) + g;
-                                    float w0[J], w1[J];
-                                    load_entry(bufH + (2 * t) * SA + k * JA, bufH + 8 * SA + (2 * t) * SB + k * JB, w0);
-                                    load_entry(bufH + (2 * t + 1) * SA + k * JA, bufH + 8 * SA + (2 * t + 1) * SB + k * JB, w1);
-#pragma unroll
-                                    for (int c = 0; c < J; ++c) {
-                                        if (XBF_W) {                          // k slots 2t, 2t+1 = points 2t, 2t+1
-                                            const uint32_t h0 = tf32_rna(w0[c]), h1 = tf32_rna(w1[c]);
-                                            bhi[b][c][PDL_L][0] = h0; bhi[b][c][PDL_L][1] = h1;
-                                            blo[b][c][PDL_L][0] = pack_bf16(w0[c], w1[c]);
-                                            blo[b][c][PDL_L][1] = pack_bf16(w0[c] - u2f(h0), w1[c] - u2f(h1));
-                                        } else {
-                                            split_tf32_raw(w0[c], bhi[b][c][PDL_L][0], blo[b][c][PDL_L][0]);
-                                            split_tf32_raw(w1[c], bhi[b][c][PDL_L][1], blo[b][c][PDL_L][1]);
-                                        }
-                                    }
-                                }
+                        for (int b = 0; b < NTB; ++b) {
+                            if (nt0 + b < NT8) make_b(b, nt0 + b);
+                            PDL_FOR_LANES {
 #pragma unroll
                                 for (int q = 0; q < NACW; ++q) { c4[b][q][PDL_L][0] = 0.f; c4[b][q][PDL_L][1] = 0.f; c4[b][q][PDL_L][2] = 0.f; c4[b][q][PDL_L][3] = 0.f; }
                             }
@@ -928,6 +910,42 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                     stg4(q, r);
                 }
             }
+        };
+        auto dgrad_layer = [&](const int l) {
+            const float* Wd = sm + SM_HH + (l - 1) * HH_SIZE + HH_WD;
+            PDL_FOR_LANES {
+                const int pg = lane >> 2, g4 = lane & 3;
+                // ---- data gradient on the FP32 pipe: hb[p][k] = sum_n zb[p][n] * W[n][k]   (k = the lane's own neurons)
+                if (!DGRAD_MMA) {
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) {
+#pragma unroll
+                    for (int c = 0; c < J; ++c) hb[PDL_L][i][c] = 0.f;
+                }
+                const float* zA = bufZ + pg * SA;
+                const float* zB = bufZ + 8 * SA + pg * SB;
+#pragma unroll 2
+                for (int nc = 0; nc < WP; nc += 4) {
+                    float a[4][J];
+#pragma unroll
+                    for (int nn = 0; nn < 4; ++nn) load_entry(zA + (nc + nn) * JA, zB + (nc + nn) * JB, a[nn]);
+#pragma unroll
+                    for (int nn = 0; nn < 4; ++nn) {
+                        const float* wr = Wd + (nc + nn) * SD + g4 * GS;
+                        float w[NPL];
+#pragma unroll
+                        for (int i = 0; i + 3 < NPL; i += 4) { const pdl_f4 t = ld4(wr + i); w[i] = t.x; w[i + 1] = t.y; w[i + 2] = t.z; w[i + 3] = t.w; }
+                        if ((NPL & 3) >= 2) { const pdl_f2 t = ld2(wr + (NPL & ~3)); w[(NPL & ~3)] = t.x; w[(NPL & ~3) + 1 < NPL ? (NPL & ~3) + 1 : 0] = t.y; }
+                        if (NPL & 1) w[NPL - 1] = wr[NPL - 1];
+#pragma unroll
+                        for (int i = 0; i < NPL; ++i) {
+#pragma unroll
+                            for (int c = 0; c < J; ++c) hb[PDL_L][i][c] += a[nn][c] * w[i];
+                        }
+                    }
+                }
+                }
+            }
             if (DGRAD_MMA) {
                 // ---- data gradient on the tensor pipe: hb = zb W, A fragments straight from the registers, B = W^T hi/lo
                 const float* Thi = sm + SM_HH + (l - 1) * HH_SIZE + HH_THI;
@@ -950,9 +968,9 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                     PDL_FOR_LANES {
 #pragma unroll
                         for (int m = 0; m < NM; ++m) {
-                            const float v0 = zbk[PDL_L][2 * s][2 * m], v2 = zbk[PDL_L][2 * s + 1][2 * m];
-                            const float v1 = (2 * m + 1 < J) ? zbk[PDL_L][2 * s][(2 * m + 1 < J) ? 2 * m + 1 : 0] : 0.f;
-                            const float v3 = (2 * m + 1 < J) ? zbk[PDL_L][2 * s + 1][(2 * m + 1 < J) ? 2 * m + 1 : 0] : 0.f;
+                            const float v0 = hb[PDL_L][2 * s][2 * m], v2 = hb[PDL_L][2 * s + 1][2 * m];
+                            const float v1 = (2 * m + 1 < J) ? hb[PDL_L][2 * s][(2 * m + 1 < J) ? 2 * m + 1 : 0] : 0.f;
+                            const float v3 = (2 * m + 1 < J) ? hb[PDL_L][2 * s + 1][(2 * m + 1 < J) ? 2 * m + 1 : 0] : 0.f;
                             if (XBF_D) split_cross(v0, v1, v2, v3, ahi[m][PDL_L], alo[m][PDL_L]);
                             else {
                                 split_tf32_dg(v0, ahi[m][PDL_L][0], alo[m][PDL_L][0]);
@@ -1003,7 +1021,98 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                     }
                 }
             }
+        };
+        auto store_zb = [&]() {                      // hb[] (= zb of the current layer) -> bufZ
+            PDL_FOR_LANES {
+                const int pg = lane >> 2, g4 = lane & 3;
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) {
+                    const int n = own_neuron(g4, i);
+                    store_entry(bufZ + pg * SA + n * JA, bufZ + 8 * SA + pg * SB + n * JB, hb[PDL_L][i]);
+                }
+            }
+        };
+        auto reduce_rational = [&](float (&ga)[PDL_NL][7], const int layer) {
+#if PDL_ACT == 1
+            xor_add<7>(ga, 1); xor_add<7>(ga, 2); xor_add<7>(ga, 4); xor_add<7>(ga, 8); xor_add<7>(ga, 16);
+            PDL_FOR_LANES { if (lane == 0) { for (int q = 0; q < 7; ++q) sacc[SO_RAT + layer * 7 + q] += ga[PDL_L][q]; } }
+#else
+            (void)ga; (void)layer;
+#endif
+        };
+        if (ADJ_FUSED && H >= 2) {                   // top hidden layer: zb_{H-1} = act'(z_{H-1}, hb_{H-1}) in place
+            float ga[PDL_NL][7];
+            PDL_FOR_LANES {
+#pragma unroll
+                for (int q = 0; q < 7; ++q) ga[PDL_L][q] = 0.f;
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) {
+                    float z[J], zb[J];
+                    scratch_load(zs, H - 2, i, lane, z);
+                    act_adjoint(z, hb[PDL_L][i], sm + SM_RAT + (H - 1) * 8, zb, ga[PDL_L]);
+#pragma unroll
+                    for (int c = 0; c < J; ++c) hb[PDL_L][i][c] = zb[c];
+                }
+            }
+            store_zb();                              // read by the weight gradient (after the next __syncwarp) and by the FP32-pipe data gradient
+            reduce_rational(ga, H - 1);
+            if (!DGRAD_MMA) PDL_SYNCWARP();
+        }
+        if (!ADJ_FUSED) {
+            for (int l = H - 1; l >= 1; --l) {
+                float ga[PDL_NL][7];
+                PDL_FOR_LANES {
+                    const int pg = lane >> 2, g4 = lane & 3;
+#pragma unroll
+                    for (int q = 0; q < 7; ++q) ga[PDL_L][q] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < NPL; ++i) {
+                        const int n = own_neuron(g4, i);
+                        float z[J], zb[J];
+                        scratch_load(zs, l - 1, i, lane, z);
+                        act_adjoint(z, hb[PDL_L][i], sm + SM_RAT + l * 8, zb, ga[PDL_L]);
+                        store_entry(bufZ + pg * SA + n * JA, bufZ + 8 * SA + pg * SB + n * JB, zb);
+#pragma unroll
+                        for (int c = 0; c < J; ++c) hb[PDL_L][i][c] = zb[c];
+                        // activations of the layer below (input of this linear layer), recomputed
+                        float zi[J], hi[J];
+                        if (l >= 2) scratch_load(zs, l - 2, i, lane, zi);
+                        else layer0_preact(sm, n, x[PDL_L], zi);
+                        act_forward(zi, sm + SM_RAT + (l - 1) * 8, hi);
+                        store_entry(bufH + pg * SA + n * JA, bufH + 8 * SA + pg * SB + n * JB, hi);
+                    }
+                }
+                PDL_SYNCWARP();
+                reduce_rational(ga, l);
+                wgrad_layer(l);
+                dgrad_layer(l);
+                PDL_SYNCWARP();
+            }
+        }
+        for (int l = H - 1; ADJ_FUSED && l >= 1; --l) {
+            dgrad_layer(l);                          // hb: zb_l -> hb_{l-1}
+            float ga[PDL_NL][7];
+            PDL_FOR_LANES {
+                const int pg = lane >> 2, g4 = lane & 3;
+#pragma unroll
+                for (int q = 0; q < 7; ++q) ga[PDL_L][q] = 0.f;
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) {
+                    const int n = own_neuron(g4, i);
+                    float zi[J], hi[J], zb[J];
+                    if (l >= 2) scratch_load(zs, l - 2, i, lane, zi);
+                    else layer0_preact(sm, n, x[PDL_L], zi);
+                    act_forward_adjoint(zi, hb[PDL_L][i], sm + SM_RAT + (l - 1) * 8, hi, zb, ga[PDL_L]);
+                    store_entry(bufH + pg * SA + n * JA, bufH + 8 * SA + pg * SB + n * JB, hi);
+#pragma unroll
+                    for (int c = 0; c < J; ++c) hb[PDL_L][i][c] = zb[c];
+                }
+            }
+            reduce_rational(ga, l - 1);
             PDL_SYNCWARP();
+            wgrad_layer(l);                          // bufZ = zb_l, bufH = h_{l-1}
+            PDL_SYNCWARP();
+            if (l >= 2) { store_zb(); if (!DGRAD_MMA) PDL_SYNCWARP(); }   // the tensor-pipe data gradient reads hb[], not bufZ
         }
         // ---------------- layer 0 adjoint ----------------
         {
@@ -1016,9 +1125,15 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
 #pragma unroll
                 for (int i = 0; i < NPL; ++i) {
                     const int n = own_neuron(g4, i);
-                    float z[J], zb[J];
-                    layer0_preact(sm, n, x[PDL_L], z);
-                    act_adjoint(z, hb[PDL_L][i], sm + SM_RAT, zb, ga[PDL_L]);
+                    float zb[J];
+                    if (ADJ_FUSED && H >= 2) {         // zb_0 was produced in place by the last pass of the loop above
+#pragma unroll
+                        for (int c = 0; c < J; ++c) zb[c] = hb[PDL_L][i][c];
+                    } else {
+                        float z[J];
+                        layer0_preact(sm, n, x[PDL_L], z);
+                        act_adjoint(z, hb[PDL_L][i], sm + SM_RAT, zb, ga[PDL_L]);
+                    }
 #pragma unroll
                     for (int dd = 0; dd < D; ++dd) {
                         float t = zb[0] * x[PDL_L][dd];
@@ -1031,7 +1146,7 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
             }
             xor_add<NPL*(D + 1)>(g0, 4); xor_add<NPL*(D + 1)>(g0, 8); xor_add<NPL*(D + 1)>(g0, 16);
 #if PDL_ACT == 1
-            xor_add<7>(ga, 1); xor_add<7>(ga, 2); xor_add<7>(ga, 4); xor_add<7>(ga, 8); xor_add<7>(ga, 16);
+            if (!(ADJ_FUSED && H >= 2)) { xor_add<7>(ga, 1); xor_add<7>(ga, 2); xor_add<7>(ga, 4); xor_add<7>(ga, 8); xor_add<7>(ga, 16); }
 #endif
             PDL_FOR_LANES {
                 const int pg = lane >> 2, g4 = lane & 3;
@@ -1045,7 +1160,7 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                     }
                 }
 #if PDL_ACT == 1
-                if (lane == 0) { for (int q = 0; q < 7; ++q) sacc[SO_RAT + q] += ga[PDL_L][q]; }
+                if (!(ADJ_FUSED && H >= 2) && lane == 0) { for (int q = 0; q < 7; ++q) sacc[SO_RAT + q] += ga[PDL_L][q]; }
 #endif
             }
         }

@@ -241,9 +241,15 @@ std::string generate_plan_source(const PlanSpec& spec, PlanMeta* meta_out) {
             if (meta.dgrad_mma == 1 && smem_floats(meta, nw) * 4 > 227 * 1024) meta.dgrad_mma = 2;
         }
         if (meta.dgrad_mma == 1 && smem_floats(meta, nw) * 4 > 227 * 1024) meta.dgrad_mma = 2;
-        // weight gradient on the tensor pipe: measured faster everywhere except Rational nets that also run the data gradient there
-        // (register pressure; heat 5.44 -> 5.81 ms, burgers 7.08 -> 7.74 ms), see experiments/README.md
-        meta.wgrad_mma = (spec.wgrad_mma >= 0) ? (spec.wgrad_mma ? 1 : 0) : ((spec.activation == 1 && meta.dgrad_mma) ? 0 : 1);
+        // weight gradient on the tensor pipe: faster or equal everywhere (Rational nets with the W^T-copy data gradient used to lose
+        // to register pressure; with the bf16 cross terms and MUFU.RCP it is a tie: heat 4.16 vs 4.20 ms, burgers 5.63 vs 5.62; Rational
+        // J = 6: KS 7.87 -> 7.17 ms), see experiments/README.md
+        meta.wgrad_mma = (spec.wgrad_mma >= 0) ? (spec.wgrad_mma ? 1 : 0) : 1;
+        // order of the hidden-layer adjoint: the fused order (data gradient, then one activation pass shared by the recomputed
+        // forward and the adjoint, then the weight gradient, with a rolled m-tile loop) saves one tanh / Rational recurrence per
+        // neuron and layer and is 3-17 % faster everywhere except tanh nets with J <= 4, where the classic order with the unrolled
+        // m-tile loop wins by 5 % (heat: 3.04 vs 3.16-3.21 ms; a register-allocation effect, measured in both directions)
+        meta.adj_fused = (spec.adj_fused >= 0) ? (spec.adj_fused ? 1 : 0) : ((spec.activation == 0 && J <= 4) ? 0 : 1);
         // cross terms hi*lo + lo*hi of the split products as ONE bf16 m16n8k16 MMA (2 tensor-pipe instructions per product instead of
         // 3); bit mask: 1 = forward, 2 = data gradient, 4 = weight gradient.  Default 6: measured 8-11 % faster with unchanged parity
         // errors; the forward (bit 1) would gain another 3-7 % but its errors reach 1.4e-5 on the derivative features (gate: 1e-5).
@@ -268,7 +274,8 @@ std::string generate_plan_source(const PlanSpec& spec, PlanMeta* meta_out) {
       << "\n#define PDL_K " << K << "\n#define PDL_ACT " << spec.activation << "\n#define PDL_NS " << NS
       << "\n#define PDL_NW " << nw << "\n#define PDL_MODE " << spec.mode << "\n#define PDL_SF " << meta.sf
       << "\n#define PDL_GS " << meta.gs << "\n#define PDL_DGRAD_MMA " << meta.dgrad_mma
-      << "\n#define PDL_WGRAD_MMA " << meta.wgrad_mma << "\n#define PDL_CROSS_BF16 " << meta.cross_bf16 << "\n";
+      << "\n#define PDL_WGRAD_MMA " << meta.wgrad_mma << "\n#define PDL_CROSS_BF16 " << meta.cross_bf16
+      << "\n#define PDL_ADJ_FUSED " << meta.adj_fused << "\n#define PDL_WGRAD_ROLL_MT " << ((J >= 5 || meta.adj_fused) ? 1 : 0) << "\n";
     o << "#ifdef PDL_EMULATE\n#define PDL_GEN static inline\n#else\n#define PDL_GEN __host__ __device__ __forceinline__\n#endif\n";
 
     // widths / first-order component -> axis

@@ -94,6 +94,8 @@ static int desc_to_spec(const pdl_plan_desc* d, pdl_host::PlanSpec* s) {
     if (dg && *dg) s->dgrad_mma = atoi(dg);
     const char* wg = getenv("PDL_WGRAD_MMA");
     if (wg && *wg) s->wgrad_mma = atoi(wg);
+    const char* af = getenv("PDL_ADJ_FUSED");
+    if (af && *af) s->adj_fused = atoi(af);
     const char* xb = getenv("PDL_CROSS_BF16");
     if (xb && *xb) s->cross_bf16 = atoi(xb);
     const char* eng = getenv("PDL_ENGINE");

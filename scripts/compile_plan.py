@@ -21,7 +21,7 @@ with tempfile.TemporaryDirectory() as td:
     cu = os.path.join(td, "plan.cu")
     open(cu, "w").write(src)
     r = subprocess.run(["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xptxas", "-v", "--shared",
-                        "-Xcompiler", "-fPIC", "-I" + csrc, "-o", os.path.join(td, "p.so"), cu], capture_output=True, text=True)
+                        "-Xcompiler", "-fPIC", "-I" + csrc] + os.environ.get("PDL_NVCC_FLAGS", "").split() + ["-o", os.path.join(td, "p.so"), cu], capture_output=True, text=True)
     lines = (r.stdout + r.stderr).splitlines()
     for i, l in enumerate(lines):
         if "pdl_main_kernel" in l and "Compiling" in l or "registers" in l or "spill" in l:

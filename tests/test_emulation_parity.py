@@ -150,6 +150,28 @@ def test_emulated_bf16_cross_term_variants(name, dgrad, wgrad, cross, tol, monke
     assert rel_max(out["grad_xi"], g.z["grad_xi"]) <= tol
 
 
+@pytest.mark.parametrize("fused", ["0", "1"])
+@pytest.mark.parametrize("name,dgrad,wgrad", [("heat_tanh", "1", "1"), ("heat_rational", "0", "0"), ("ks_tanh", "2", "1"),
+                                              ("wave_mixed_tanh", "0", "1"), ("burgers_rational20", "1", "0"), ("heat3d_tanh", "2", "0")])
+def test_emulated_adjoint_orders(name, dgrad, wgrad, fused, monkeypatch):
+    """PDL_ADJ_FUSED: the classic order of the hidden-layer adjoint (adjoint of layer l and recompute of layer l-1 in one loop, then
+    weight gradient, then data gradient) and the fused order (data gradient, one activation pass shared by the recomputed forward and
+    the adjoint, weight gradient), each with tensor-pipe and FP32-pipe contractions.  The plan compiler picks per plan."""
+    monkeypatch.setenv("PDL_ENGINE", "mma")
+    monkeypatch.setenv("PDL_DGRAD_MMA", dgrad)
+    monkeypatch.setenv("PDL_WGRAD_MMA", wgrad)
+    monkeypatch.setenv("PDL_ADJ_FUSED", fused)
+    g = GoldenCase(name)
+    desc, keep = desc_for(g)
+    assert "#define PDL_ADJ_FUSED %s\n" % fused in L.plan_source(desc)
+    out = emu.run_emu(desc, g.points.numpy(), [p.numpy() for p in g.params], g.xi.numpy(), np.array(g.mask, dtype=np.uint8), n_ctas=2)
+    want = float(g.z["coll_loss"])
+    assert abs(out["loss"] - want) <= TOL * want
+    assert rel_max(out["residual"], g.z["residual"]) <= TOL
+    assert rel_max(out["grad_params"], np.concatenate([x.numpy().ravel() for x in g.grads])) <= TOL
+    assert rel_max(out["grad_xi"], g.z["grad_xi"]) <= TOL
+
+
 @pytest.mark.parametrize("name", ["heat_tanh", "ks_rational"])
 def test_emulated_device_row_count(name):
     """The row count read from memory (pdl_launch_args.n_points_dev, captured epochs): a launch over the whole buffer with the count
