@@ -422,16 +422,30 @@ PDL_DEV void rational_param_adjoint(float z0, const float* rp, const float (&r)[
 }
 #endif
 
-// forward activation of one neuron: jets z -> jets h
-PDL_DEV void act_forward(const float (&z)[J], const float* rp, float (&h)[J]) {
+#ifndef PDL_TANH_CACHE
+#define PDL_TANH_CACHE 0
+#endif
+// tanh nets: keep tanh(z0) of the layer whose adjoint comes next in a register per neuron (the forward pass / the recompute of the
+// layer below evaluates it anyway), so the adjoint's activation derivatives cost the polynomials only
+constexpr bool TANH_CACHE = (PDL_ACT == 0) && (PDL_TANH_CACHE != 0);
+
+// forward activation of one neuron: jets z -> jets h; tc receives tanh(z0) (tanh nets)
+PDL_DEV void act_forward(const float (&z)[J], const float* rp, float (&h)[J], float& tc) {
     float s[NS], r[NS], inv;
     sigmas(z[0], rp, s, r, inv);
+    tc = s[0];
     pdl_act_fwd(z, s, h);
 }
-// adjoint of one neuron's activation: (z, hb) -> zb ; accumulates rational coefficient gradients
-PDL_DEV void act_adjoint(const float (&z)[J], const float (&hb)[J], const float* rp, float (&zb)[J], float (&ga)[7]) {
+// adjoint of one neuron's activation: (z, hb) -> zb ; accumulates rational coefficient gradients; tc = cached tanh(z0) if TANH_CACHE
+PDL_DEV void act_adjoint(const float (&z)[J], const float (&hb)[J], const float* rp, float (&zb)[J], float (&ga)[7], const float tc) {
     float s[NS], r[NS], inv, sb[NS - 1];
+#if PDL_ACT == 0
+    if (TANH_CACHE) { (void)r; inv = 0.f; pdl_tanh_sigmas(tc, s); }
+    else sigmas(z[0], rp, s, r, inv);
+#else
+    (void)tc;
     sigmas(z[0], rp, s, r, inv);
+#endif
     pdl_act_adj(z, hb, s, zb, sb);
     float z0b = 0.f;
 #pragma unroll
@@ -567,6 +581,7 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
     float uu[PDL_NL][J];
     float ub[PDL_NL][J];
     float valid[PDL_NL];
+    float tcache[PDL_NL][NPL];        // tanh(z0) of the layer whose adjoint comes next (TANH_CACHE)
     bool first = true;
 
     for (long long tile = gwarp; tile < n_tiles; tile += n_warps, first = false) {
@@ -581,7 +596,7 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
             for (int i = 0; i < NPL; ++i) {
                 float z[J];
                 layer0_preact(sm, own_neuron(g4, i), x[PDL_L], z);
-                act_forward(z, sm + SM_RAT, h[PDL_L][i]);
+                act_forward(z, sm + SM_RAT, h[PDL_L][i], tcache[PDL_L][i]);
             }
         }
         // ---------------- hidden -> hidden layers, forward ----------------
@@ -653,7 +668,7 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
 #pragma unroll
                     for (int c = 0; c < J; ++c) z[c] = accf[i >> 1][c >> 1][PDL_L][2 * (c & 1) + (i & 1)];
                     if (BWD) scratch_store(zs, l - 1, i, lane, z);
-                    act_forward(z, sm + SM_RAT + l * 8, h[PDL_L][i]);
+                    act_forward(z, sm + SM_RAT + l * 8, h[PDL_L][i], tcache[PDL_L][i]);
                 }
             }
         }
@@ -1049,7 +1064,7 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                 for (int i = 0; i < NPL; ++i) {
                     float z[J], zb[J];
                     scratch_load(zs, H - 2, i, lane, z);
-                    act_adjoint(z, hb[PDL_L][i], sm + SM_RAT + (H - 1) * 8, zb, ga[PDL_L]);
+                    act_adjoint(z, hb[PDL_L][i], sm + SM_RAT + (H - 1) * 8, zb, ga[PDL_L], tcache[PDL_L][i]);
 #pragma unroll
                     for (int c = 0; c < J; ++c) hb[PDL_L][i][c] = zb[c];
                 }
@@ -1070,7 +1085,7 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                         const int n = own_neuron(g4, i);
                         float z[J], zb[J];
                         scratch_load(zs, l - 1, i, lane, z);
-                        act_adjoint(z, hb[PDL_L][i], sm + SM_RAT + l * 8, zb, ga[PDL_L]);
+                        act_adjoint(z, hb[PDL_L][i], sm + SM_RAT + l * 8, zb, ga[PDL_L], tcache[PDL_L][i]);
                         store_entry(bufZ + pg * SA + n * JA, bufZ + 8 * SA + pg * SB + n * JB, zb);
 #pragma unroll
                         for (int c = 0; c < J; ++c) hb[PDL_L][i][c] = zb[c];
@@ -1078,7 +1093,7 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                         float zi[J], hi[J];
                         if (l >= 2) scratch_load(zs, l - 2, i, lane, zi);
                         else layer0_preact(sm, n, x[PDL_L], zi);
-                        act_forward(zi, sm + SM_RAT + (l - 1) * 8, hi);
+                        act_forward(zi, sm + SM_RAT + (l - 1) * 8, hi, tcache[PDL_L][i]);
                         store_entry(bufH + pg * SA + n * JA, bufH + 8 * SA + pg * SB + n * JB, hi);
                     }
                 }
@@ -1132,7 +1147,7 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                     } else {
                         float z[J];
                         layer0_preact(sm, n, x[PDL_L], z);
-                        act_adjoint(z, hb[PDL_L][i], sm + SM_RAT, zb, ga[PDL_L]);
+                        act_adjoint(z, hb[PDL_L][i], sm + SM_RAT, zb, ga[PDL_L], tcache[PDL_L][i]);
                     }
 #pragma unroll
                     for (int dd = 0; dd < D; ++dd) {

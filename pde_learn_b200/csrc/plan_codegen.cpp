@@ -275,7 +275,10 @@ std::string generate_plan_source(const PlanSpec& spec, PlanMeta* meta_out) {
       << "\n#define PDL_NW " << nw << "\n#define PDL_MODE " << spec.mode << "\n#define PDL_SF " << meta.sf
       << "\n#define PDL_GS " << meta.gs << "\n#define PDL_DGRAD_MMA " << meta.dgrad_mma
       << "\n#define PDL_WGRAD_MMA " << meta.wgrad_mma << "\n#define PDL_CROSS_BF16 " << meta.cross_bf16
-      << "\n#define PDL_ADJ_FUSED " << meta.adj_fused << "\n#define PDL_WGRAD_ROLL_MT " << ((J >= 5 || meta.adj_fused) ? 1 : 0) << "\n";
+      << "\n#define PDL_ADJ_FUSED " << meta.adj_fused << "\n#define PDL_WGRAD_ROLL_MT " << ((J >= 5 || meta.adj_fused) ? 1 : 0)
+      // tanh(z0) cached in a register per neuron for the next adjoint: +1-2 % with the fused order (kdv 4.19 -> 4.09 ms), -4 % for
+      // the classic-order J <= 4 kernels (heat 3.03 -> 3.16 ms: spills)
+      << "\n#define PDL_TANH_CACHE " << ((spec.activation == 0 && meta.adj_fused) ? 1 : 0) << "\n";
     o << "#ifdef PDL_EMULATE\n#define PDL_GEN static inline\n#else\n#define PDL_GEN __host__ __device__ __forceinline__\n#endif\n";
 
     // widths / first-order component -> axis
