@@ -864,11 +864,15 @@ int pdl_k_launch(const pdl::Params* P, int n_ctas, int bwd, float* grad_params, 
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     const bool devn = P->n_points_dev != nullptr;
+    // opt-in (PDL_L2_PERSIST=1): the collocation adjoint's workspace in a persisting L2 window, see kernel_params.h
+    const PdlL2Window win = (bwd && PDL_MODE == 0) ? pdl_l2_window(P, n_ctas, dev) : PdlL2Window{nullptr, 0, 0.f};
+    pdl_l2_window_apply(st, win, true);
     if (bwd && !devn) pdl_main_kernel<true, false><<<n_ctas, pdl::NT, pdl::SM_TOTAL * 4, st>>>(*P);
     else if (bwd) pdl_main_kernel<true, true><<<n_ctas, pdl::NT, pdl::SM_TOTAL * 4, st>>>(*P);
     else if (!devn) pdl_main_kernel<false, false><<<n_ctas, pdl::NT, pdl::SM_TOTAL * 4, st>>>(*P);
     else pdl_main_kernel<false, true><<<n_ctas, pdl::NT, pdl::SM_TOTAL * 4, st>>>(*P);
     cudaError_t e = cudaGetLastError();
+    pdl_l2_window_apply(st, win, false);
     if (e != cudaSuccess) return (int)e;
     pdl::ReduceArgs R;
     R.cta_out = P->cta_out; R.cta_stats = P->cta_stats; R.n_ctas = n_ctas;
