@@ -1383,7 +1383,7 @@ int pdl_k_launch(const pdl::Params* P, int n_ctas, int bwd, float* grad_params, 
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     const bool devn = P->n_points_dev != nullptr;
-    // opt-in (PDL_L2_PERSIST=1): the collocation adjoint's workspace in a persisting L2 window, see kernel_params.h
+    // the collocation adjoint's workspace in a persisting L2 window for the duration of this launch, see kernel_params.h
     const PdlL2Window win = (bwd && PDL_MODE == 0) ? pdl_l2_window(P, n_ctas, dev) : PdlL2Window{nullptr, 0, 0.f};
     pdl_l2_window_apply(st, win, true);
     if (bwd && !devn) pdl_main_kernel<true, false><<<n_ctas, pdl::NT, pdl::SM_TOTAL * 4, st>>>(*P);

@@ -20,14 +20,16 @@ struct PdlKernelParams {
 
 #if defined(__CUDACC__) && !defined(PDL_EMULATE)
 #include <cstdlib>
-// ---- optional: L2 persistence for the workspace (PDL_L2_PERSIST=1, off by default) -----------------------------------------
+// ---- L2 persistence for the workspace (on for launches of >= 2^15 rows; PDL_L2_PERSIST=0 switches it off) -----------------
 // Every 8-point tile rewrites its warp's adjoint scratch and read-modify-writes its weight-gradient partial sums: ~62-75 MB that
 // never leave the L2 (hit rate 99.2 %), but whose dirty lines the L2 keeps writing back to DRAM in the background -- 2.4 GB (heat)
-// to 6.1 GB (KS) per 2^20-row launch.  Marking the workspace as *persisting* inside an L2 set-aside stops that: measured 2.42 GB ->
-// 12.8 MB (heat) and 6.08 GB -> 7.7 MB (KS) written per launch with the window set as a stream attribute before the launch and
-// cleared after it (profiles/r01g_*).  It stays opt-in because the time effect is not robust: heat +3.5 %, KS -3 %, others 0 in
-// that form; the same window as a launch attribute (cudaLaunchKernelEx) or set once and left on the stream turned every workspace
-// store into a DRAM write instead (7.0 GB, +17-19 % on heat), and each cudaStreamSetAttribute costs ~35 us of host time.
+// to 6.4 GB (KS) per 2^20-row launch, 150-400x the algorithmic traffic.  Marking the workspace as *persisting* inside an L2
+// set-aside stops that: measured 2.42 GB -> 5.7-12.8 MB (heat) and 6.40 GB -> 7.1 MB (KS) written per launch, on two boxes, with the
+// window set as a stream attribute before the launch and cleared after it (profiles/r01g_*, r01h_*).  Kernel time: heat +2.6-3.5 %,
+// KS -2.3-3 %, others 0; whole closure heat -1.2 %.  Two variants that must NOT be used (measured): the same window as a launch
+// attribute (cudaLaunchKernelEx) or set once and left on the stream turned every workspace store into a DRAM write (7.0 GB,
+// +17-19 % on heat).  Each cudaStreamSetAttribute costs ~35 us of host time, hence the row threshold.  A failure of any of the
+// optional calls degrades to a plain launch.
 struct PdlL2Window { void* base; size_t bytes; float ratio; };
 static inline PdlL2Window pdl_l2_window(const PdlKernelParams* P, int n_ctas, int dev) {
     static int state[64] = {0};                  // 0 = not probed, 1 = usable, 2 = off
@@ -38,14 +40,14 @@ static inline PdlL2Window pdl_l2_window(const PdlKernelParams* P, int n_ctas, in
         state[dev] = 2;
         const char* e = getenv("PDL_L2_PERSIST");
         int a = 0, b = 0;
-        if (e && e[0] == '1' && cudaDeviceGetAttribute(&a, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess &&
+        if (!(e && e[0] == '0') && cudaDeviceGetAttribute(&a, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess &&
             cudaDeviceGetAttribute(&b, cudaDevAttrMaxAccessPolicyWindowSize, dev) == cudaSuccess && a > 0 && b > 0 &&
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)a) == cudaSuccess) {
             setaside[dev] = (size_t)a; winmax[dev] = (size_t)b; state[dev] = 1;
         }
         (void)cudaGetLastError();
     }
-    if (state[dev] != 1 || !P->zscratch || !P->cta_stats) return w;
+    if (state[dev] != 1 || !P->zscratch || !P->cta_stats || P->n_points < (1 << 15)) return w;
     // per-warp scratch + weight-gradient partial sums + per-CTA records are contiguous in the workspace
     const size_t bytes = (size_t)((const char*)P->cta_stats - (const char*)P->zscratch) + (size_t)n_ctas * 4 * sizeof(double);
     w.base = P->zscratch;
