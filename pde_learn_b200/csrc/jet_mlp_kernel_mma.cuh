@@ -1055,6 +1055,7 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
             (void)ga; (void)layer;
 #endif
         };
+        // ---------------- hidden layers adjoint: activation passes (top layer, classic and fused loops) ----------------
         if (ADJ_FUSED && H >= 2) {                   // top hidden layer: zb_{H-1} = act'(z_{H-1}, hb_{H-1}) in place
             float ga[PDL_NL][7];
             PDL_FOR_LANES {

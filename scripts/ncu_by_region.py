@@ -1,7 +1,7 @@
 """Attribute the warp-stall samples / executed instructions of an `ncu --set full --import-source on` capture of pdl_main_kernel to
 the regions of warp_body() in jet_mlp_kernel_mma.cuh (no GPU needed): ncu's SASS source page is joined by instruction offset with
-`nvdisasm --print-line-info-inline` of the same plan module compiled here; an instruction belongs to the outermost line of its
-inline chain that lies inside warp_body (so helpers count for their call site).
+`nvdisasm --print-line-info-inline` of the same plan module compiled here; an instruction belongs to the innermost line of its
+inline chain that lies inside warp_body (helpers defined outside count for their call site; lambda bodies count as themselves).
 usage: python scripts/ncu_by_region.py report.ncu-rep plan.so [--lines N]"""
 import collections
 import csv
@@ -30,7 +30,7 @@ with tempfile.TemporaryDirectory() as td:
     cub = [f for f in os.listdir(td) if f.endswith(".cubin")][0]
     dis = subprocess.run(["nvdisasm", "--print-line-info-inline", os.path.join(td, cub)], capture_output=True, text=True).stdout.splitlines()
 line_of = {}          # offset -> line in warp_body (or None)
-on = False; chain = []
+on = False; chain = []; chain_open = False
 for l in dis:
     if l.startswith(".text."):
         on = "pdl_main_kernelILb1ELb0" in l; chain = []
@@ -39,7 +39,7 @@ for l in dis:
         continue
     m = re.match(r'\s*//## File "([^"]+)", line (\d+)', l)
     if m:
-        if "inlined at" not in l and chain and not chain_open:
+        if not chain_open:                       # first location line after an instruction: a new chain (innermost first)
             chain = []
         chain_open = True
         chain.append((m.group(1), int(m.group(2))))
@@ -48,7 +48,7 @@ for l in dis:
     if m:
         chain_open = False
         inside = [ln for f, ln in chain if f.endswith("jet_mlp_kernel_mma.cuh") and body0 <= ln < body1]
-        line_of[int(m.group(1), 16)] = inside[-1] if inside else None
+        line_of[int(m.group(1), 16)] = inside[0] if inside else None      # innermost line inside warp_body (lambda bodies included)
 rows = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout.splitlines()))
 hdr = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 H = rows[hdr]
