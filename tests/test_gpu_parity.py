@@ -485,3 +485,37 @@ def test_fp32_pipe_engine_parity_subprocess():
     env = dict(os.environ, PDL_ENGINE="ffma")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "ENGINE_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])
+
+
+VARIANT_CODE = (
+    "import sys, numpy as np, torch\n"
+    "sys.path.insert(0, %r)\n"
+    "import pde_learn_b200 as P\n"
+    "from tests.helpers import GoldenCase, rel_max\n"
+    "from tests.test_gpu_parity import _network_from_golden, _terms\n"
+    "tol = float(sys.argv[1])\n"
+    "for name in ('heat_tanh', 'ks_rational'):\n"
+    "    g = GoldenCase(name); U = _network_from_golden(g, P); derivs, lhs, rhs = _terms(P, g.lhs, g.rhs)\n"
+    "    xi = g.xi.to('cuda').requires_grad_(True)\n"
+    "    loss, r = P.Coll_Loss(U, xi, torch.tensor(g.mask), g.points.to('cuda'), derivs, lhs, rhs); loss.backward()\n"
+    "    got = np.concatenate([p.grad.cpu().numpy().ravel() for p in U.parameters()])\n"
+    "    ref = np.concatenate([x.numpy().ravel() for x in g.grads])\n"
+    "    assert abs(float(loss.detach()) - float(g.z['coll_loss'])) <= tol * float(g.z['coll_loss'])\n"
+    "    assert rel_max(r.cpu().numpy(), g.z['residual']) <= tol and rel_max(got, ref) <= tol\n"
+    "    assert rel_max(xi.grad.cpu().numpy(), g.z['grad_xi']) <= tol\n"
+    "print('VARIANT_OK')\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+# the non-default code paths of the tensor-pipe engine (the plan compiler's defaults are covered by every other test):
+# plain 3xTF32 everywhere, the other order of the hidden-layer adjoint for both fixtures, bf16 cross terms in the forward pass too
+KERNEL_VARIANTS = [({"PDL_CROSS_BF16": "0"}, 1e-5), ({"PDL_ADJ_FUSED": "1"}, 1e-5), ({"PDL_ADJ_FUSED": "0"}, 1e-5),
+                   ({"PDL_CROSS_BF16": "7"}, 3e-5)]
+
+
+@pytest.mark.parametrize("env,tol", KERNEL_VARIANTS)
+def test_tensor_pipe_kernel_variants_subprocess(env, tol):
+    """Kernel variants selected by the PDL_* knobs run on the device through the public API (fresh process: plans are cached per
+    process and the knobs are read when a plan is created); __graft_entry__.build() pre-compiles their plans."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, "-c", VARIANT_CODE, str(tol)], capture_output=True, text=True, env=dict(os.environ, **env), timeout=600)
+    assert r.returncode == 0 and "VARIANT_OK" in r.stdout, (env, r.stdout[-2000:], r.stderr[-3000:])
