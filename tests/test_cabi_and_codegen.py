@@ -95,3 +95,29 @@ def test_sampler_and_lp_argument_checks():
     assert rc != 0 and "Bounds" in L.lib().pdl_last_error().decode()
     rc = L.lib().pdl_lp_loss(None, None, 3, 2.5, None, None, None)
     assert rc != 0 and "0 < p < 2" in L.lib().pdl_last_error().decode()
+
+
+def test_build_menu_covers_the_golden_fixtures():
+    """__graft_entry__.build() pre-compiles, for every golden fixture, the collocation plan and the Evaluate_Derivatives plan exactly
+    as the host layer will request them (same derivative order), so the GPU box does not have to run nvcc for the parity tests."""
+    import __graft_entry__ as G
+    import pde_learn_b200 as P
+    from pde_learn_b200 import engine as E
+    from pde_learn_b200.Term import Term
+    from tests.helpers import GOLDEN_CASES, GoldenCase
+    import numpy as np
+
+    def terms_of(g):
+        from oracle import pde_oracle as O
+        mk = lambda t: P.Term([P.Derivative(np.array(e)) for e, _ in t], [p for _, p in t])
+        return [P.Derivative(np.array(e)) for e in O.distinct_encodings(g.lhs, g.rhs)], mk(g.lhs), [mk(t) for t in g.rhs]
+
+    menu = {repr((m[0], list(m[1]), m[2], m[3], [tuple(e) for e in m[4]], [[tuple(x) for x in t] for t in m[5]])) for m in G._plan_menu()}
+    for name in GOLDEN_CASES:
+        g = GoldenCase(name)
+        derivs, lhs, rhs = terms_of(g)
+        act = L.PDL_ACT_RATIONAL if g.activation == "rational" else L.PDL_ACT_TANH
+        for a, b in ((lhs, rhs), (Term([derivs[0]], [1]), [Term([D], [1]) for D in derivs[1:]])):
+            encs, terms = E.library_key(derivs, a, b)
+            key = repr((g.d, [int(v) for v in g.widths], act, L.PDL_MODE_COLLOCATION, [tuple(e) for e in encs], [[tuple(x) for x in t] for t in terms]))
+            assert key in menu, (name, key)
