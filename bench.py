@@ -324,6 +324,10 @@ def run_ours(args):
             exe = mma_flops_pt * B / (k_ms * 1e-3) / 1e12
             roofline["tensor_pipe"] = {"executed_tflops": exe, "peak": 277.0, "frac": exe / 277.0, "mma_per_tile_layer": per_layer,
                                        "mma_per_product": per_prod,
+                                       # transparency: the same algorithmic flops against the tcgen05-class dense TF32 peak (half of the
+                                       # measured bf16 rate in MEASURED_PEAKS.json) -- a pipe this kernel does not use at width 40
+                                       "algorithmic_frac_of_tcgen05_tf32_peak": (achieved_tf / (float(peaks["bf16_tflops_sustained"]) / 2.0)
+                                                                                 if peaks.get("bf16_tflops_sustained") else None),
                                        "contractions_on_tensor_pipe": ["forward"] + (["dgrad"] if df["PDL_DGRAD_MMA"] else []) +
                                                                       (["wgrad"] if df["PDL_WGRAD_MMA"] else []),
                                        "peak_source": "mma.sync.m16n8k8 TF32 microbenchmark, profiles/r01_ubench.txt (277 TFLOP/s = "
