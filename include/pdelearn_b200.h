@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define PDL_ABI_VERSION 2
+#define PDL_ABI_VERSION 3
 
 #define PDL_ACT_TANH 0      /* torch.nn.Tanh            (Code/Classes/Network.py:161-162) */
 #define PDL_ACT_RATIONAL 1  /* Rational (3,2), trainable (Code/Classes/Network.py:7-59)   */
@@ -129,15 +129,23 @@ int pdl_sample_points(const double* bounds, int32_t d, int64_t n, uint64_t seed,
 int pdl_sample_points_dev(const double* bounds, int32_t d, int64_t n, const uint64_t* seed_dev, uint64_t first_index,
                           float* out, void* stream);
 
+/* The Philox4x32-10 block function the sampler is built on, exposed for known-answer tests (Random123 kat_vectors):
+ * counters_keys: device uint32 [n][6] = counter[4], key[2]; out: device uint32 [n][4].  pdl_sample_points uses
+ * counter = {row index low, high, 0, 0}, key = {seed low, high} and turns word j into coordinate j as
+ * min(fma((word >> 8) * 2^-24, hi_j - lo_j, lo_j), hi_j). */
+int pdl_philox4x32_10_raw(const uint32_t* counters_keys, int64_t n, uint32_t* out, void* stream);
+
 /* Targeted collocation points (Code/main.py:365-384): sum and sum of squares of |r| over the first
- * n_random rows (stats: device double[2]) and compaction of rows with |r| >= cutoff (order preserved).
+ * n_random rows (stats: device double[4]; [0], [1] = the sums, [2], [3] = scratch; two-stage reduction in a fixed
+ * order, no floating-point atomics: deterministic) and compaction of rows with |r| >= cutoff (order preserved).
  * out_count: device int64[1]; out_points must hold n rows; block_scratch: device int32[(n+1023)/1024 + 1]. */
 int pdl_abs_residual_moments(const float* residual, int64_t n_random, double* stats, void* stream);
 int pdl_select_targeted(const float* points, const float* residual, int64_t n, int32_t d, float cutoff,
                         float* out_points, int64_t* out_count, int32_t* block_scratch, void* stream);
 /* The whole update without a host round trip: moments over the first n_random rows, cutoff = mean + 3*std
  * (unbiased) computed on the device, then the compaction.  stats: device double[4] (sum|r|, sum r^2, cutoff as
- * float in stats[2], reserved). */
+ * float in stats[2], and in stats[3] the number of selected rows BEFORE clamping to the output capacity, as an int64 bit
+ * pattern: selected > capacity means rows were dropped). */
 int pdl_targeted_update(const float* points, const float* residual, int64_t n, int64_t n_random, int32_t d,
                         float* out_points, int64_t* out_count, double* stats, int32_t* block_scratch, void* stream);
 

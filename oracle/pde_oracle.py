@@ -308,3 +308,53 @@ def config_library(name: str) -> Tuple[int, TermSpec, List[TermSpec], List[Tuple
         return (3, [(Vt, 1)], monomials(s, 1) + monomials(s, 2) + [[(V, 3)]],
                 [(0.0, 5.0), (-5.0, 5.0), (-5.0, 5.0)])
     raise KeyError(name)
+
+
+# ----------------------------------------------------------------------------------------------
+# Point sampler: Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11; the Random123
+# library's philox4x32 with 10 rounds).  The reference samples with Python's random.uniform (Code/Points.py:45-57),
+# which a counter-based device sampler cannot reproduce; what is pinned here is the published block function, by
+# Random123's own known-answer vectors (tests/test_oracle_vs_golden.py), and the word -> coordinate map the CUDA
+# sampler documents in include/pdelearn_b200.h.
+# ----------------------------------------------------------------------------------------------
+PHILOX_KAT = [   # (counter[4], key[2]) -> output[4]   (Random123 tests/kat_vectors, philox4x32 10 rounds)
+    ((0x00000000, 0x00000000, 0x00000000, 0x00000000), (0x00000000, 0x00000000), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+    ((0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff), (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+    ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+]
+
+
+def philox4x32_10(counter, key):
+    """counter: uint32 [n, 4], key: uint32 [n, 2] -> uint32 [n, 4] (numpy, vectorised over n)."""
+    import numpy as np
+    c = np.asarray(counter, dtype=np.uint64).reshape(-1, 4).copy()
+    k = np.asarray(key, dtype=np.uint64).reshape(-1, 2).copy()
+    mask = np.uint64(0xFFFFFFFF)
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85)
+    s32 = np.uint64(32)
+    for _ in range(10):
+        p0, p1 = M0 * c[:, 0], M1 * c[:, 2]
+        hi0, lo0, hi1, lo1 = p0 >> s32, p0 & mask, p1 >> s32, p1 & mask
+        c = np.stack([hi1 ^ c[:, 1] ^ k[:, 0], lo1, hi0 ^ c[:, 3] ^ k[:, 1], lo0], axis=1)
+        k = np.stack([(k[:, 0] + W0) & mask, (k[:, 1] + W1) & mask], axis=1)
+    return c.astype(np.uint32)
+
+
+def sample_points(bounds, n: int, seed: int, first_index: int = 0):
+    """The CUDA sampler restated: row i uses counter = {(first_index + i) low, high, 0, 0}, key = {seed low, high}; word j becomes
+    coordinate j = min(fma(float(word >> 8) * 2^-24, hi_j - lo_j, lo_j), hi_j) in float32.  Returns float32 [n, d]."""
+    import numpy as np
+    b = np.asarray(bounds, dtype=np.float64).reshape(-1, 2)
+    d = b.shape[0]
+    idx = np.arange(n, dtype=np.uint64) + np.uint64(first_index)
+    ctr = np.zeros((n, 4), dtype=np.uint64)
+    ctr[:, 0], ctr[:, 1] = idx & np.uint64(0xFFFFFFFF), idx >> np.uint64(32)
+    key = np.empty((n, 2), dtype=np.uint64)
+    key[:, 0], key[:, 1] = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    w = philox4x32_10(ctr, key)
+    lo32, hi32 = b[:, 0].astype(np.float32), b[:, 1].astype(np.float32)
+    span = (hi32 - lo32).astype(np.float32)
+    u = (w[:, :d] >> np.uint32(8)).astype(np.float64) * 2.0 ** -24            # exact
+    # fused multiply-add in float32 = the exactly computed product plus lo, rounded once; float64 holds the 48-bit product exactly
+    out = (u * span.astype(np.float64) + lo32.astype(np.float64)).astype(np.float32)
+    return np.minimum(out, hi32[None, :])

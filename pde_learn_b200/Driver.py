@@ -23,11 +23,14 @@ from .Test_Train import Testing, Training
 THRESHOLD = 0.0005           # Code/main.py:31
 
 
-def Update_Targeted_Points(Coll_Points: torch.Tensor, Residual: torch.Tensor, Num_Random: int) -> torch.Tensor:
+def Update_Targeted_Points(Coll_Points: torch.Tensor, Residual: torch.Tensor, Num_Random: int, Process_Group=None) -> torch.Tensor:
     """
     Rows of Coll_Points whose |residual| >= mean + 3*std, the moments taken over the first Num_Random rows
     (the freshly sampled points) and the selection over all rows, order preserved (Code/main.py:365-384).
     Everything runs on the device; only the number of kept rows is read back.
+    With `Process_Group` the rows are this rank's shard: sum |r|, sum r^2 and the row count of the random rows are all-reduced
+    (3 doubles) so that every rank applies the cutoff of the GLOBAL batch -- the targeted set is then the same for any number of
+    ranks -- and each rank compacts its own shard.
     """
     P = Coll_Points.detach()
     r = Residual.detach()
@@ -40,10 +43,28 @@ def Update_Targeted_Points(Coll_Points: torch.Tensor, Residual: torch.Tensor, Nu
     cnt = torch.zeros(1, dtype=torch.int64, device=P.device)
     stats = torch.zeros(4, dtype=torch.float64, device=P.device)
     scratch = torch.empty((n + 1023) // 1024 + 1, dtype=torch.int32, device=P.device)
+    stream = torch.cuda.current_stream(P.device).cuda_stream
     with torch.cuda.device(P.device):
-        L.check(L.lib().pdl_targeted_update(P.data_ptr(), r.data_ptr(), n, int(Num_Random), d, out.data_ptr(), cnt.data_ptr(),
-                                            stats.data_ptr(), scratch.data_ptr(), torch.cuda.current_stream(P.device).cuda_stream))
+        if Process_Group is None:
+            L.check(L.lib().pdl_targeted_update(P.data_ptr(), r.data_ptr(), n, int(Num_Random), d, out.data_ptr(), cnt.data_ptr(),
+                                                stats.data_ptr(), scratch.data_ptr(), stream))
+        else:
+            import torch.distributed as dist
+            L.check(L.lib().pdl_abs_residual_moments(r.data_ptr(), int(Num_Random), stats.data_ptr(), stream))
+            glob = torch.stack([stats[0], stats[1], torch.tensor(float(Num_Random), dtype=torch.float64, device=P.device)])
+            dist.all_reduce(glob, group=Process_Group)
+            s1, s2, m = (float(v) for v in glob.cpu())
+            cutoff = targeted_cutoff(s1, s2, m)
+            L.check(L.lib().pdl_select_targeted(P.data_ptr(), r.data_ptr(), n, d, C.c_float(cutoff), out.data_ptr(), cnt.data_ptr(),
+                                                scratch.data_ptr(), stream))
     return out[:int(cnt.item())]
+
+
+def targeted_cutoff(sum_abs: float, sum_sq: float, count: float) -> float:
+    """mean + 3 * unbiased std of |r| from its sums (Code/main.py:369-380), rounded to float32 like the device cutoff kernel."""
+    mean = sum_abs / count if count > 0 else 0.0
+    var = (sum_sq - count * mean * mean) / (count - 1.0) if count > 1 else 0.0
+    return float(numpy.float32(mean + 3.0 * numpy.sqrt(max(var, 0.0))))
 
 
 def Build_Mask(Xi: torch.Tensor, Threshold: float = THRESHOLD) -> torch.Tensor:
@@ -71,16 +92,32 @@ def Run_Epochs(U_List: List[Network], Xi: torch.Tensor, Mask: torch.Tensor, Inpu
     `Use_CUDA_Graph=True` (Adam, one process, default sampler) replays the whole epoch as one captured CUDA graph
     (Epoch_Graph.Captured_Epochs): same numbers, no per-epoch host work; epochs are replayed in chunks of 10 unless Testing
     is requested every epoch.
+    `Process_Group` (one process per GPU): the epoch's Num_Train_Coll_Points random rows and the data rows are SHARDED -- rank g
+    draws global rows [g*n, (g+1)*n) of the same Philox stream (n = Num_Train_Coll_Points / world, which must divide), takes its
+    slice of Inputs/Targets, keeps the targeted points of its own shard, and the targeted cutoff uses the all-reduced moments:
+    the numbers equal the one-process run at 1/world of the work per rank.  A user `Point_Sampler` receives the per-rank count
+    and must return this rank's rows.
     """
     S = len(U_List)
     dev = Xi.device
     d = int(Bounds_List[0].shape[0])
+    rank, world = 0, 1
+    if Process_Group is not None:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(Process_Group), dist.get_world_size(Process_Group)
+        if Num_Train_Coll_Points % world or (Num_Test_Coll_Points % world):
+            raise ValueError("Num_Train_Coll_Points and Num_Test_Coll_Points must be multiples of the world size (%d)" % world)
+        shard = lambda T: T[rank * (T.shape[0] // world):(rank + 1) * (T.shape[0] // world) if rank + 1 < world else T.shape[0]].contiguous()
+        Inputs_List = [shard(X) for X in Inputs_List]
+        Targets_List = [shard(Y) for Y in Targets_List]
+    n_loc, n_test_loc = Num_Train_Coll_Points // world, Num_Test_Coll_Points // world
     targeted = [torch.empty((0, d), dtype=torch.float32, device=dev) for _ in range(S)]
     hist = {"Train Coll": numpy.zeros((Num_Epochs, S)), "Train Data": numpy.zeros((Num_Epochs, S)),
             "Train Total": numpy.zeros((Num_Epochs, S)), "L2": numpy.zeros((Num_Epochs, S)), "Lp": numpy.zeros(Num_Epochs),
             "Test Coll": numpy.zeros((Num_Epochs, S)), "Test Data": numpy.zeros((Num_Epochs, S)),
             "Num Targeted": numpy.zeros((Num_Epochs, S), dtype=numpy.int64)}
-    sample = Point_Sampler or (lambda i, e, n: Generate_Points(Bounds_List[i], n, dev, Seed=(Seed * 1000003 + e) * 64 + i))
+    sample = Point_Sampler or (lambda i, e, n: Generate_Points(Bounds_List[i], n, dev, Seed=(Seed * 1000003 + e) * 64 + i,
+                                                               First_Index=rank * n))
     if Use_CUDA_Graph:
         if Point_Sampler is not None or Process_Group is not None:
             raise ValueError("Use_CUDA_Graph works with the built-in sampler in one process")
@@ -88,7 +125,7 @@ def Run_Epochs(U_List: List[Network], Xi: torch.Tensor, Mask: torch.Tensor, Inpu
         cap = Captured_Epochs(U_List, Xi, Mask, Inputs_List, Targets_List, Bounds_List, Derivatives, LHS_Term, RHS_Terms, p, Weights,
                               Optimizer, Num_Train_Coll_Points, Max_Targeted=Max_Targeted, Seed=Seed)
         chunk = 1 if Num_Test_Coll_Points > 0 else 10
-        e = 0
+        e = drained = 0
         while e < Num_Epochs:
             m = min(chunk, Num_Epochs - e)
             cap.run(m)
@@ -97,8 +134,9 @@ def Run_Epochs(U_List: List[Network], Xi: torch.Tensor, Mask: torch.Tensor, Inpu
                 te = Testing(U_List, Xi, Mask, tp, Test_Inputs_List or Inputs_List, Test_Targets_List or Targets_List, Derivatives,
                              LHS_Term, RHS_Terms, p, Weights)
                 hist["Test Coll"][e] = te["Coll Losses"]; hist["Test Data"][e] = te["Data Losses"]
-            if On_Epoch is not None or e + m >= Num_Epochs:
-                h = cap.history()
+            if On_Epoch is not None or e + m >= Num_Epochs or (e + m - drained) + chunk > cap.hcap:
+                h = cap.history()                       # drained at least once per History_Capacity epochs (ring buffer)
+                drained = e + m
                 a = e + m - h["Lp"].shape[0]
                 for key in ("Train Coll", "Train Data", "Train Total", "L2", "Lp", "Num Targeted"):
                     hist[key][a:e + m] = h[key]
@@ -108,19 +146,19 @@ def Run_Epochs(U_List: List[Network], Xi: torch.Tensor, Mask: torch.Tensor, Inpu
             e += m
         return hist
     for e in range(Num_Epochs):
-        coll = [torch.vstack((sample(i, e, Num_Train_Coll_Points).to(dev), targeted[i])) for i in range(S)]
+        coll = [torch.vstack((sample(i, e, n_loc).to(dev), targeted[i])) for i in range(S)]
         tr = Training(U_List, Xi, Mask, coll, Inputs_List, Targets_List, Derivatives, LHS_Term, RHS_Terms, p, Weights, Optimizer,
                       Process_Group=Process_Group, Residuals_Device="cuda")
         hist["Train Coll"][e] = tr["Coll Losses"]; hist["Train Data"][e] = tr["Data Losses"]
         hist["Train Total"][e] = tr["Total Losses"]; hist["L2"][e] = tr["L2 Losses"]; hist["Lp"][e] = tr["Lp Loss"]
         if Num_Test_Coll_Points > 0:
-            tp = [sample(i, Num_Epochs + e, Num_Test_Coll_Points).to(dev) for i in range(S)]
+            tp = [sample(i, Num_Epochs + e, n_test_loc).to(dev) for i in range(S)]
             te = Testing(U_List, Xi, Mask, tp, Test_Inputs_List or Inputs_List, Test_Targets_List or Targets_List, Derivatives,
-                         LHS_Term, RHS_Terms, p, Weights)
+                         LHS_Term, RHS_Terms, p, Weights)          # per-rank means over this rank's test rows
             hist["Test Coll"][e] = te["Coll Losses"]; hist["Test Data"][e] = te["Data Losses"]
         for i in range(S):
-            targeted[i] = Update_Targeted_Points(coll[i], tr["Residuals"][i], Num_Train_Coll_Points)
-            hist["Num Targeted"][e, i] = targeted[i].shape[0]
+            targeted[i] = Update_Targeted_Points(coll[i], tr["Residuals"][i], n_loc, Process_Group=Process_Group)
+            hist["Num Targeted"][e, i] = targeted[i].shape[0]          # this rank's share
         if On_Epoch is not None:
             On_Epoch(e, hist)
     return hist

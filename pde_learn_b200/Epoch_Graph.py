@@ -171,7 +171,8 @@ class Captured_Epochs:
                                                     self.tcount[i].data_ptr(), self.tstats[i].data_ptr(), self.tscratch[i].data_ptr(), stream))
                 self.coll[i][N:].copy_(self.tbuf[i])
                 torch.add(self.tcount[i], N, out=self.count[i])
-            nt = torch.cat(self.tcount).to(torch.float64)
+            # rows selected before clamping to the carry-over capacity (stats[3], int64 bit pattern): history() raises when rows were lost
+            nt = torch.cat([st[3:4].view(torch.int64) for st in self.tstats]).to(torch.float64)
             row = torch.cat([coll, data, l2d, totals, nt, lpd]).unsqueeze(0)
             self.hist.index_copy_(0, self.epoch_dev % self.hcap, row)
             self.epoch_dev += 1
@@ -232,8 +233,11 @@ class Captured_Epochs:
         self._read = self._done
         out = {"Train Coll": h[:, 0:S], "Train Data": h[:, S:2 * S], "L2": h[:, 2 * S:3 * S], "Train Total": h[:, 3 * S:4 * S],
                "Num Targeted": h[:, 4 * S:5 * S].astype(numpy.int64), "Lp": h[:, 5 * S]}
-        if out["Num Targeted"].size and int(out["Num Targeted"].max()) >= self.cap_t:
-            raise RuntimeError("targeted-point capacity (%d rows) reached: rebuild with a larger Max_Targeted" % self.cap_t)
+        if out["Num Targeted"].size and int(out["Num Targeted"].max()) > self.cap_t:
+            first = int(numpy.argmax(out["Num Targeted"].max(axis=1) > self.cap_t))
+            raise RuntimeError("targeted-point capacity exceeded: epoch %d selected %d rows, %d can be carried over; the epochs after "
+                               "it trained on a truncated set -- rebuild with a larger Max_Targeted"
+                               % (self._read - h.shape[0] + first, int(out["Num Targeted"].max()), self.cap_t))
         return out
 
     def targeted_points(self, i: int = 0) -> torch.Tensor:

@@ -73,12 +73,9 @@ def Training(U_List: List, Xi: torch.Tensor, Mask: torch.Tensor, Coll_Points_Lis
         total, scalars, residuals = closure_total(U_List, Xi, Mask, Coll_Points_List, Inputs_List, Targets_List, Derivatives,
                                                   LHS_Term, RHS_Terms, p, Weights,
                                                   inv_n_coll=[1.0 / max(n, 1) for n in n_coll],
-                                                  inv_n_data=[1.0 / max(n, 1) for n in n_data], world=world)
+                                                  inv_n_data=[1.0 / max(n, 1) for n in n_data], world=world, group=Process_Group)
         if total.requires_grad:
-            total.backward()
-            if Process_Group is not None:
-                params = [q for U in U_List for q in U.parameters()] + [Xi]
-                allreduce_gradients(params, Process_Group)
+            total.backward()          # with a process group the closure node all-reduces its flat gradient buffer itself
         last.update(scalars=scalars, residuals=residuals)
         return total.reshape(1)
 

@@ -58,6 +58,7 @@ PROTOTYPES = {
     "pdl_sample_points_dev": (C.c_int, [C.POINTER(C.c_double), C.c_int32, C.c_int64, C.c_void_p, C.c_uint64,
                                         C.c_void_p, C.c_void_p]),
     "pdl_abs_residual_moments": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "pdl_philox4x32_10_raw": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pdl_select_targeted": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdl_targeted_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
@@ -94,7 +95,7 @@ def lib():
             fn = getattr(handle, name)            # AttributeError here = header/library mismatch
             fn.restype = res
             fn.argtypes = args
-        if handle.pdl_abi_version() != 2:
+        if handle.pdl_abi_version() != 3:
             raise NativeLibraryError("libpdelearn_b200.so ABI version mismatch")
         _lib = handle
     return _lib

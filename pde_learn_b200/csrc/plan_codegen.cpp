@@ -260,6 +260,15 @@ std::string generate_plan_source(const PlanSpec& spec, PlanMeta* meta_out) {
         if (meta.dgrad_mma == 2 && (meta.cross_bf16 & 1)) meta.cross_bf16 |= 2;
         if (meta.dgrad_mma == 2 && (meta.cross_bf16 & 2) && smem_floats(meta, nw) * 4 > 227 * 1024) meta.cross_bf16 &= ~3;
     }
+    // launches without gradients on the tcgen05 / TMEM forward engine (jet_mlp_fwd_tc.cuh) when the jet set fits the 512 tensor-memory
+    // columns: two accumulator sets (J components at a pitch of NP, or WP with overlapping padding columns) + one or two ring slots
+    meta.fwd_tc = 0;
+    if (meta.engine == 1 && spec.mode == 0 && H >= 2 && spec.fwd_tc != 0) {
+        const int NP = (WP + 15) / 16 * 16, SLOT = 16 * J;
+        const bool roomy = 2 * NP * J + 2 * SLOT <= 512;
+        const int dcols = (roomy ? NP : WP) * (J - 1) + NP;
+        if (2 * dcols + SLOT <= 512) meta.fwd_tc = 1;
+    }
     while (nw > 1 && smem_floats(meta, nw) * 4 > 227 * 1024) --nw;
     if (smem_floats(meta, nw) * 4 > 227 * 1024) throw std::runtime_error("plan does not fit in shared memory");
     meta.nw = nw;
@@ -416,7 +425,15 @@ std::string generate_plan_source(const PlanSpec& spec, PlanMeta* meta_out) {
         }
         o << "}\n";
     }
-    o << (meta.engine == 1 ? "#include \"jet_mlp_kernel_mma.cuh\"\n" : "#include \"jet_mlp_kernel.cuh\"\n");
+    if (meta.fwd_tc) {
+        // the tcgen05 forward engine wraps the module's entry points: it takes the launches without gradients and forwards the rest
+        // (the mma.sync template itself stays untouched, so plans without this engine keep their cached modules)
+        o << "#define PDL_FWD_TC 1\n#ifndef PDL_EMULATE\n#define pdl_k_launch pdl_k_launch_mma\n#define pdl_k_info pdl_k_info_mma\n#endif\n"
+          << "#include \"jet_mlp_kernel_mma.cuh\"\n#ifndef PDL_EMULATE\n#undef pdl_k_launch\n#undef pdl_k_info\n#endif\n"
+          << "#include \"jet_mlp_fwd_tc.cuh\"\n";
+    } else {
+        o << (meta.engine == 1 ? "#include \"jet_mlp_kernel_mma.cuh\"\n" : "#include \"jet_mlp_kernel.cuh\"\n");
+    }
     if (meta_out) *meta_out = meta;
     return o.str();
 }

@@ -22,12 +22,13 @@ struct PlanSpec {
     int engine = -1;                                         // -1 = choose, 0 = FP32-pipe kernel, 1 = tensor-pipe (mma.sync) kernel
     int adj_fused = -1;                                      // tensor-pipe engine: order of the hidden-layer adjoint (-1 = choose)
     int cross_bf16 = -1;                                     // tensor-pipe engine: hi*lo + lo*hi as ONE bf16 m16n8k16 MMA (-1 = choose)
+    int fwd_tc = -1;                                         // launches without gradients on the tcgen05/TMEM forward engine (-1 = if it fits)
 };
 
 struct PlanMeta {
     int d = 0, n_jets = 0, n_rhs = 0, hidden_layers = 0, wp = 0, max_order = 0, mode = 0, activation = 0;
     int n_param_tensors = 0, n_param_scalars = 0, sf = 0, gs = 0, nw = 0, smem_bytes = 0;
-    int engine = 0, dgrad_mma = 0, wgrad_mma = 0, cross_bf16 = 0, adj_fused = 0, tile_points = 8;
+    int engine = 0, dgrad_mma = 0, wgrad_mma = 0, cross_bf16 = 0, adj_fused = 0, tile_points = 8, fwd_tc = 0;
     long long flops_per_point = 0;
     std::vector<std::array<int, 4>> jets;
 };

@@ -11,7 +11,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/file.h>
 #include <sys/stat.h>
+#include <fcntl.h>
 #include <unistd.h>
 
 #include <fstream>
@@ -98,6 +100,8 @@ static int desc_to_spec(const pdl_plan_desc* d, pdl_host::PlanSpec* s) {
     if (af && *af) s->adj_fused = atoi(af);
     const char* xb = getenv("PDL_CROSS_BF16");
     if (xb && *xb) s->cross_bf16 = atoi(xb);
+    const char* tc = getenv("PDL_FWD_TC");
+    if (tc && *tc) s->fwd_tc = atoi(tc);
     const char* eng = getenv("PDL_ENGINE");
     if (eng && *eng) s->engine = (eng[0] == 'm' || eng[0] == 'M' || eng[0] == '1') ? 1 : 0;
     return 0;
@@ -133,32 +137,46 @@ int pdl_plan_create(const pdl_plan_desc* desc, pdl_plan** out) {
         const std::string src = pdl_host::generate_plan_source(spec, &meta);
         const std::string cdir = csrc_dir(), pdir = plans_dir();
         const std::string hdr = read_file(cdir + (meta.engine == 1 ? "/jet_mlp_kernel_mma.cuh" : "/jet_mlp_kernel.cuh")) +
-                                read_file(cdir + "/kernel_params.h");
+                                read_file(cdir + "/kernel_params.h") + (meta.fwd_tc ? read_file(cdir + "/jet_mlp_fwd_tc.cuh") : std::string());
         if (hdr.size() < 100) return fail("kernel template not found in " + cdir + " (set PDL_CSRC_DIR)");
         const char* xf = getenv("PDL_NVCC_FLAGS");
         const std::string flags = std::string("-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo ") + (xf ? xf : "");
+        const char* nv = getenv("PDL_NVCC");
+        const std::string nvcc = (nv && *nv) ? nv : "/usr/local/cuda/bin/nvcc";
+        // the cache key covers the generated source, the flags, the kernel templates and the toolkit this library was built with
+        // (a stale module must not survive a toolkit upgrade); the compiler path is part of it too
         char hx[32];
-        snprintf(hx, sizeof hx, "%016llx", (unsigned long long)pdl_host::fnv1a(src + "\n//" + flags + "\n" + hdr));
+        snprintf(hx, sizeof hx, "%016llx", (unsigned long long)pdl_host::fnv1a(src + "\n//" + flags + "\n//cuda " + std::to_string(CUDART_VERSION) +
+                                                                                " " + nvcc + "\n" + hdr));
         const std::string base = pdir + "/plan_" + hx;
         const std::string so = base + ".so";
-        static std::mutex mu;
+        static std::mutex mu;                              // threads of this process
         std::lock_guard<std::mutex> lock(mu);
         if (!file_exists(so)) {
             mkdir(pdir.c_str(), 0755);
-            const std::string cu = base + ".cu";
-            { std::ofstream f(cu); f << src; }
-            const char* nv = getenv("PDL_NVCC");
-            const std::string nvcc = (nv && *nv) ? nv : "/usr/local/cuda/bin/nvcc";
-            const std::string tmp = base + "." + std::to_string((long long)getpid()) + ".tmp.so";
-            const std::string cmd = nvcc + " " + flags + " -Xptxas -v --shared -Xcompiler -fPIC -I" + cdir + " -o " + tmp + " " + cu +
-                                    " > " + base + ".log 2>&1";
-            const int rc = system(cmd.c_str());
-            if (rc != 0 || !file_exists(tmp)) {
-                std::string log = read_file(base + ".log");
-                if (log.size() > 2000) log = log.substr(log.size() - 2000);
-                return fail("nvcc failed for plan " + std::string(hx) + " (no fallback): " + log);
+            // ranks that start together all miss on the same plan: one of them compiles, the others wait on the directory lock
+            // and find the installed module.  Source, log and module are written under per-process names and renamed into place.
+            const std::string lockp = pdir + "/.lock";
+            const int lfd = open(lockp.c_str(), O_CREAT | O_RDWR, 0644);
+            if (lfd >= 0) flock(lfd, LOCK_EX);
+            struct Unlock { int fd; ~Unlock() { if (fd >= 0) { flock(fd, LOCK_UN); close(fd); } } } unlock{lfd};
+            if (!file_exists(so)) {
+                const std::string pid = std::to_string((long long)getpid());
+                const std::string cu_tmp = base + "." + pid + ".tmp.cu", log_tmp = base + "." + pid + ".tmp.log", tmp = base + "." + pid + ".tmp.so";
+                { std::ofstream f(cu_tmp); f << src; }
+                auto q = [](const std::string& x) { std::string r = "'"; for (char c : x) { if (c == '\'') r += "'\\''"; else r += c; } return r + "'"; };
+                const std::string cmd = q(nvcc) + " " + flags + " -Xptxas -v --shared -Xcompiler -fPIC -I" + q(cdir) + " -o " + q(tmp) + " " +
+                                        q(cu_tmp) + " > " + q(log_tmp) + " 2>&1";
+                const int rc = system(cmd.c_str());
+                if (rc != 0 || !file_exists(tmp)) {
+                    std::string log = read_file(log_tmp);
+                    if (log.size() > 2000) log = log.substr(log.size() - 2000);
+                    return fail("nvcc failed for plan " + std::string(hx) + " (no fallback): " + log);
+                }
+                rename(cu_tmp.c_str(), (base + ".cu").c_str());
+                rename(log_tmp.c_str(), (base + ".log").c_str());
+                if (rename(tmp.c_str(), so.c_str()) != 0 && !file_exists(so)) return fail("could not install " + so);
             }
-            if (rename(tmp.c_str(), so.c_str()) != 0 && !file_exists(so)) return fail("could not install " + so);
         }
         void* h = dlopen(so.c_str(), RTLD_NOW | RTLD_LOCAL);
         if (!h) return fail(std::string("dlopen failed: ") + dlerror());
@@ -320,6 +338,18 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
     const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
     c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
 }
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) { philox_round(c, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+}
+// raw Philox4x32-10 blocks (known-answer tests, Random123 kat_vectors): in [n][6] = counter[4], key[2]; out [n][4]
+__global__ void philox_raw_kernel(const uint32_t* __restrict__ in, long long n, uint32_t* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t c[4] = {in[6 * i], in[6 * i + 1], in[6 * i + 2], in[6 * i + 3]};
+    philox4x32_10(c, in[6 * i + 4], in[6 * i + 5]);
+    for (int j = 0; j < 4; ++j) out[4 * i + j] = c[j];
+}
 struct SampleArgs { float lo[4]; float span[4]; float hi[4]; };
 __global__ void sample_kernel(const SampleArgs A, int d, long long n, unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
                               unsigned long long first, float* __restrict__ out) {
@@ -328,9 +358,7 @@ __global__ void sample_kernel(const SampleArgs A, int d, long long n, unsigned l
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const unsigned long long idx = first + (unsigned long long)i;
         uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), 0u, 0u};
-        uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
-        for (int r = 0; r < 10; ++r) { philox_round(c, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
         for (int j = 0; j < d; ++j) {
             const float u = (float)(c[j] >> 8) * (1.0f / 16777216.0f);          // [0, 1)
             out[i * d + j] = fminf(fmaf(u, A.span[j], A.lo[j]), A.hi[j]);
@@ -339,7 +367,10 @@ __global__ void sample_kernel(const SampleArgs A, int d, long long n, unsigned l
 }
 
 // ---- targeted collocation points (Code/main.py:365-384) ----
-__global__ void moments_kernel(const float* __restrict__ r, long long n, double* __restrict__ stats) {
+// Two stages, no floating-point atomics: block b sums its grid-strided rows in a fixed order and writes (sum |r|, sum r^2) to
+// partial[b]; one warp then adds the partials in index order.  Two launches over the same rows give the same bits, so the targeted
+// cutoff is deterministic like everything else on the path.
+__global__ void moments_partial_kernel(const float* __restrict__ r, long long n, double* __restrict__ partial) {
     double s1 = 0.0, s2 = 0.0;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -353,8 +384,15 @@ __global__ void moments_kernel(const float* __restrict__ r, long long n, double*
     if (threadIdx.x == 0) {
         double a = 0.0, b = 0.0;
         for (int w = 0; w < (blockDim.x + 31) / 32; ++w) { a += p1[w]; b += p2[w]; }
-        atomicAdd(&stats[0], a); atomicAdd(&stats[1], b);
+        partial[2 * blockIdx.x] = a; partial[2 * blockIdx.x + 1] = b;
     }
+}
+__global__ void moments_final_kernel(const double* __restrict__ partial, int nb, double* __restrict__ stats) {
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < nb; i += 32) { a += partial[2 * i]; b += partial[2 * i + 1]; }
+    // fixed butterfly order
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if (threadIdx.x == 0) { stats[0] = a; stats[1] = b; }
 }
 __global__ void cutoff_kernel(const double* __restrict__ stats, long long n_random, float* __restrict__ out) {
     // mean + 3 * unbiased std of |r| over the random rows (Code/main.py:369-380)
@@ -373,7 +411,8 @@ __global__ void select_count_kernel(const float* __restrict__ r, long long n, co
     const int c = __syncthreads_count(flag);
     if (threadIdx.x == 0) counts[blockIdx.x] = c;
 }
-__global__ void select_scan_kernel(int* __restrict__ counts, int n_blocks, long long* __restrict__ total, long long cap) {
+__global__ void select_scan_kernel(int* __restrict__ counts, int n_blocks, long long* __restrict__ total, long long cap,
+                                   long long* __restrict__ unclamped) {
     // single block: exclusive scan of counts[0..n_blocks) in place, total to *total
     __shared__ long long carry;
     __shared__ int wsum[32];
@@ -399,7 +438,7 @@ __global__ void select_scan_kernel(int* __restrict__ counts, int n_blocks, long 
         if (threadIdx.x == 1023) carry = c0 + before + x;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *total = carry < cap ? carry : cap;
+    if (threadIdx.x == 0) { *total = carry < cap ? carry : cap; if (unclamped) *unclamped = carry; }
 }
 __global__ void select_scatter_kernel(const float* __restrict__ pts, const float* __restrict__ r, long long n,
                                       const long long* __restrict__ n_dev, int d, float cutoff, const float* __restrict__ cutoff_dev,
@@ -534,13 +573,28 @@ int pdl_sample_points_dev(const double* bounds, int32_t d, int64_t n, const uint
     return sample_points_impl(bounds, d, n, 0, seed_dev, first, out, stream);
 }
 
+// partial: device scratch of 2 * max_blocks doubles (8-byte aligned)
+static int moments_impl(const float* residual, int64_t n, double* stats, double* partial, long long max_blocks, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { PDL_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(double), st)); return 0; }
+    long long blocks = (n + 4095) / 4096;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks < 1) blocks = 1;
+    moments_partial_kernel<<<(int)blocks, 1024, 0, st>>>(residual, n, partial);
+    moments_final_kernel<<<1, 32, 0, st>>>(partial, (int)blocks, stats);
+    PDL_CUDA(cudaGetLastError());
+    return 0;
+}
 int pdl_abs_residual_moments(const float* residual, int64_t n, double* stats, void* stream) {
     if (!residual || !stats || n < 0) return fail("bad arguments");
-    PDL_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(double), (cudaStream_t)stream));
+    return moments_impl(residual, n, stats, stats + 2, 1, stream);      // stats[2..3] is the one-block partial record
+}
+
+int pdl_philox4x32_10_raw(const uint32_t* counters_keys, int64_t n, uint32_t* out, void* stream) {
+    if (!counters_keys || !out || n < 0) return fail("bad arguments");
     if (n == 0) return 0;
-    long long blocks = (n + 1023) / 1024;
-    if (blocks > 148 * 4) blocks = 148 * 4;
-    moments_kernel<<<(int)blocks, 1024, 0, (cudaStream_t)stream>>>(residual, n, stats);
+    philox_raw_kernel<<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(counters_keys, n, out);
     PDL_CUDA(cudaGetLastError());
     return 0;
 }
@@ -552,7 +606,7 @@ int pdl_select_targeted(const float* points, const float* residual, int64_t n, i
     if (n == 0) { PDL_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int64_t), st)); return 0; }
     const int nb = (int)((n + 1023) / 1024);
     select_count_kernel<<<nb, 1024, 0, st>>>(residual, n, nullptr, cutoff, nullptr, block_scratch);
-    select_scan_kernel<<<1, 1024, 0, st>>>(block_scratch, nb, (long long*)out_count, n);
+    select_scan_kernel<<<1, 1024, 0, st>>>(block_scratch, nb, (long long*)out_count, n, nullptr);
     select_scatter_kernel<<<nb, 1024, 0, st>>>(points, residual, n, nullptr, d, cutoff, nullptr, block_scratch, out_points, n);
     PDL_CUDA(cudaGetLastError());
     return 0;
@@ -563,12 +617,18 @@ static int targeted_update_impl(const float* points, const float* residual, int6
     if (!out_count || !block_scratch || !stats || n < 0 || n_random < 0 || n_random > n || out_cap < 0) return fail("bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { PDL_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int64_t), st)); return 0; }
-    if (pdl_abs_residual_moments(residual, n_random, stats, stream)) return 1;
+    {   // the block scratch (int32[(n+1023)/1024 + 1], free until the selection below) hosts the per-block partial sums
+        const long long words = (n + 1023) / 1024 + 1;
+        double* partial = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(block_scratch) + 7) & ~(uintptr_t)7);
+        const long long fit = (words * 4 - 8) / 16;
+        if (fit >= 1) { if (moments_impl(residual, n_random, stats, partial, fit, stream)) return 1; }
+        else if (moments_impl(residual, n_random, stats, stats + 2, 1, stream)) return 1;
+    }
     float* cutoff_dev = reinterpret_cast<float*>(stats + 2);
     cutoff_kernel<<<1, 1, 0, st>>>(stats, n_random, cutoff_dev);
     const int nb = (int)((n + 1023) / 1024);
     select_count_kernel<<<nb, 1024, 0, st>>>(residual, n, (const long long*)n_dev, 0.f, cutoff_dev, block_scratch);
-    select_scan_kernel<<<1, 1024, 0, st>>>(block_scratch, nb, (long long*)out_count, out_cap);
+    select_scan_kernel<<<1, 1024, 0, st>>>(block_scratch, nb, (long long*)out_count, out_cap, reinterpret_cast<long long*>(stats + 3));
     select_scatter_kernel<<<nb, 1024, 0, st>>>(points, residual, n, (const long long*)n_dev, d, 0.f, cutoff_dev, block_scratch, out_points, out_cap);
     PDL_CUDA(cudaGetLastError());
     return 0;

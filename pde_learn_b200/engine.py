@@ -295,8 +295,9 @@ class ClosureSpec:
     """Everything that is not a differentiable tensor (kept out of autograd's argument handling)."""
 
     def __init__(self, U_List, Mask, Coll_Points_List, Inputs_List, Targets_List, Derivatives, LHS_Term, RHS_Terms, p, Weights,
-                 inv_n_coll, inv_n_data, world):
+                 inv_n_coll, inv_n_data, world, group=None):
         self.S = len(U_List)
+        self.group = group
         self.coll_plans = [collocation_plan(U, Derivatives, LHS_Term, RHS_Terms) for U in U_List]
         self.data_plans = [data_plan(U) for U in U_List]
         self.n_tensors = [len(network_param_tensors(U)) for U in U_List]
@@ -319,7 +320,12 @@ class _ClosureFn(torch.autograd.Function):
     """
     forward: launches Lp, and per network the fused collocation kernel, the fused data kernel and L2, then combines
     the flat gradients with the loss weights (one axpby3 pass per network).  Returns (total, scalars, *residuals):
-    scalars = [coll_0..coll_{S-1}, data_*, l2_*, total_*, lp] (float64, device).  backward only rescales.
+    scalars = [coll_0..coll_{S-1}, data_*, l2_*, total_*, lp] (float64, device).
+
+    All gradients of one closure live in ONE flat buffer  [network 0 | network 1 | ... | xi]  that the kernels write in place.
+    backward rescales that buffer once, all-reduces it once when the closure runs data-parallel (spec.group: the single collective
+    of the path) and hands autograd views of it: no split -> cat -> copy round trip, and the .grad tensors of all
+    parameters share the reduced buffer.
     """
 
     @staticmethod
@@ -334,7 +340,9 @@ class _ClosureFn(torch.autograd.Function):
         stats_d = torch.empty((S, 4), dtype=torch.float64, device=dev)
         l2 = torch.empty(S, dtype=torch.float32, device=dev)
         gx = torch.empty((S, max(K, 1)), dtype=torch.float32, device=dev) if want_grad else None
-        residuals, grads = [], []
+        n_scal = [pl.n_param_scalars for pl in spec.coll_plans]
+        flat = torch.empty(sum(n_scal) + K, dtype=torch.float32, device=dev) if want_grad else None
+        residuals, goff = [], 0
         with torch.cuda.device(dev):
             L.check(lib.pdl_lp_loss(xi.data_ptr(), spec.mask_dev.data_ptr(), K, spec.p, lp.data_ptr(), g_lp.data_ptr(), stream))
             off = 0
@@ -344,7 +352,8 @@ class _ClosureFn(torch.autograd.Function):
                 cp, dp = spec.coll_plans[i], spec.data_plans[i]
                 P = cp.n_param_scalars
                 res = torch.empty(spec.points[i].shape[0], dtype=torch.float32, device=dev)
-                gc = torch.empty(P, dtype=torch.float32, device=dev) if want_grad else None
+                gc = flat[goff:goff + P] if want_grad else None
+                goff += P
                 gd = torch.empty(P, dtype=torch.float32, device=dev) if want_grad else None
                 g2 = torch.empty(P, dtype=torch.float32, device=dev) if want_grad else None
                 cp.launch(spec.points[i], prm, xi, spec.mask_dev, None, spec.inv_n_coll[i], want_grad, res, None, gc,
@@ -358,16 +367,15 @@ class _ClosureFn(torch.autograd.Function):
                 if want_grad:
                     L.check(lib.pdl_axpby3(gc.data_ptr(), P, gc.data_ptr(), W["Coll"], gd.data_ptr(), W["Data"], g2.data_ptr(),
                                            W["L2"] / world, stream))
-                    grads.append(gc)
                 residuals.append(res)
         coll, data = stats_c[:, 0], stats_d[:, 0]
         l2d, lpd = l2.to(torch.float64), lp.to(torch.float64)
         totals = W["Data"] * data + W["Coll"] * coll + (W["Lp"] / world) * lpd + (W["L2"] / world) * l2d
         scalars = torch.cat([coll, data, l2d, totals, lpd])
-        ctx.grads = grads
-        ctx.gxi = (W["Coll"] * gx.sum(0)[:K] + (S * W["Lp"] / world) * g_lp) if want_grad else None
+        if want_grad:
+            torch.add(gx.sum(0)[:K] * W["Coll"], g_lp, alpha=S * W["Lp"] / world, out=flat[goff:goff + K])
+        ctx.flat, ctx.K, ctx.group = flat, K, spec.group
         ctx.shapes = [q.shape for q in params]
-        ctx.n_tensors = spec.n_tensors
         for r in residuals:
             ctx.mark_non_differentiable(r)
         ctx.mark_non_differentiable(scalars)
@@ -375,25 +383,28 @@ class _ClosureFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_total, _g_scalars, *_g_res):
-        if ctx.gxi is None:
+        if ctx.flat is None:
             raise RuntimeError("the closure was evaluated without gradients")
-        out, off = [], 0
-        for i, g in enumerate(ctx.grads):
-            out += _split_flat(g * g_total, ctx.shapes[off:off + ctx.n_tensors[i]])
-            off += ctx.n_tensors[i]
-        return (None, None, ctx.gxi * g_total, *out)
+        g = ctx.flat * g_total
+        if ctx.group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(g, group=ctx.group)
+        n = g.numel() - ctx.K
+        return (None, None, g[n:], *_split_flat(g[:n], ctx.shapes))
 
 
 def closure_total(U_List, Xi, Mask, Coll_Points_List, Inputs_List, Targets_List, Derivatives, LHS_Term, RHS_Terms, p, Weights,
-                  inv_n_coll=None, inv_n_data=None, world=1):
-    """(total, scalars, residuals): see _ClosureFn.  `total` is differentiable w.r.t. Xi and every network parameter."""
+                  inv_n_coll=None, inv_n_data=None, world=1, group=None):
+    """(total, scalars, residuals): see _ClosureFn.  `total` is differentiable w.r.t. Xi and every network parameter.
+    With `group` (a torch.distributed process group of `world` ranks, each holding a shard of the rows) total.backward() leaves the
+    all-reduced gradients in .grad."""
     assert torch.numel(Xi) == len(RHS_Terms)
     assert p > 0 and p < 2
     S = len(U_List)
     inv_c = inv_n_coll or [1.0 / max(int(P.shape[0]), 1) for P in Coll_Points_List]
     inv_d = inv_n_data or [1.0 / max(int(X.shape[0]), 1) for X in Inputs_List]
     spec = ClosureSpec(U_List, Mask, Coll_Points_List, Inputs_List, Targets_List, Derivatives, LHS_Term, RHS_Terms, p, Weights,
-                       inv_c, inv_d, world)
+                       inv_c, inv_d, world, group)
     params = [_check_cuda_f32(q, "network parameter") for U in U_List for q in network_param_tensors(U)]
     xi = _check_cuda_f32(Xi, "Xi")
     want = torch.is_grad_enabled() and (xi.requires_grad or any(q.requires_grad for q in params))

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), "libpdelearn_b200.so does not export %s" % s
         assert s in L.PROTOTYPES, "no ctypes prototype for %s" % s
-    assert lib.pdl_abi_version() == 2
+    assert lib.pdl_abi_version() == 3
 
 
 def _heat_desc(widths=(2, 40, 40, 40, 40, 40, 1), act=L.PDL_ACT_TANH):

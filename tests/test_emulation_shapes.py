@@ -13,21 +13,7 @@ from tests import emu
 from tests.helpers import rel_max
 
 TOL = 1e-5
-U0, Ut, Ux, Uxx = (0, 0), (1, 0), (0, 1), (0, 2)
-
-CASES = [
-    # name, d, hidden widths, activation, lhs, rhs, n points, masked
-    ("one_hidden_layer", 2, [24], "tanh", [(Ut, 1)], [[(U0, 1)], [(Uxx, 1)], [(U0, 1), (Ux, 1)]], 19, ()),
-    ("width_8", 2, [8, 8, 8], "rational", [(Ut, 1)], [[(Ux, 1)], [(Uxx, 1)]], 11, ()),
-    ("width_64", 2, [64, 64], "tanh", [(Ut, 1)], [[(Uxx, 1)], [(U0, 2)]], 9, ()),
-    ("ragged_50_12_33", 2, [50, 12, 33], "tanh", [(Ut, 1)], [[(Ux, 1)], [(U0, 1), (Uxx, 1)]], 10, ()),
-    ("value_only_J1", 2, [16, 16], "tanh", [(U0, 1)], [[(U0, 3)]], 13, ()),
-    ("no_rhs_terms_K0", 2, [16, 16], "tanh", [(Ut, 1)], [], 13, ()),
-    ("all_terms_masked", 2, [16, 16], "rational", [(Ut, 1)], [[(Ux, 1)], [(Uxx, 1)]], 13, (0, 1)),
-    ("high_powers", 2, [16, 16], "tanh", [(Ut, 2)], [[(U0, 5)], [(Ux, 3), (U0, 2)], [(Uxx, 2), (Ux, 1)]], 13, ()),
-    ("d3_mixed_xy", 3, [20, 20], "tanh", [((1, 0, 0), 1)], [[((0, 1, 1), 1)], [((0, 2, 0), 1)], [((0, 0, 0), 1), ((0, 0, 1), 1)]], 12, ()),
-    ("second_order_time", 2, [16, 16, 16], "rational", [((2, 0), 1)], [[(Uxx, 1)], [((1, 1), 1)]], 12, ()),
-]
+from tests.fixtures_meta import CASES            # plain data shared with __graft_entry__.build() (plan pre-compilation)
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])

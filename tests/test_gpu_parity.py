@@ -290,7 +290,7 @@ def test_targeted_points_and_moments():
     pts = torch.rand(n, 2, device=_dev())
     r = torch.randn(n, device=_dev())
     r[17] = 11.0; r[n - 1] = -13.0
-    st = torch.zeros(2, dtype=torch.float64, device=_dev())
+    st = torch.zeros(4, dtype=torch.float64, device=_dev())
     s = torch.cuda.current_stream().cuda_stream
     L.check(L.lib().pdl_abs_residual_moments(r.data_ptr(), n_rand, st.data_ptr(), s))
     a = r[:n_rand].abs().double()
@@ -304,6 +304,73 @@ def test_targeted_points_and_moments():
     k = int(cnt[0])
     assert k == want.shape[0]
     assert torch.equal(out[:k].cpu(), want)            # same rows, same order (bit-exact index work)
+
+
+def test_targeted_update_is_deterministic():
+    """The cutoff of the targeted update comes from a two-stage reduction in a fixed order (no floating-point atomics): repeated
+    launches give the same bits, and the kept rows equal the oracle's selection (Code/main.py:365-384)."""
+    import pde_learn_b200 as P
+    from pde_learn_b200 import _lib as L
+    torch.manual_seed(4)
+    n, n_rand = 1_200_007, 1_000_000
+    pts = torch.rand(n, 2, device=_dev())
+    r = torch.randn(n, device=_dev()) * torch.rand(n, device=_dev())
+    s = torch.cuda.current_stream().cuda_stream
+    seen = []
+    for rep in range(4):
+        out = torch.empty_like(pts); cnt = torch.zeros(1, dtype=torch.int64, device=_dev())
+        st = torch.zeros(4, dtype=torch.float64, device=_dev())
+        scratch = torch.empty((n + 1023) // 1024 + 1, dtype=torch.int32, device=_dev())
+        L.check(L.lib().pdl_targeted_update(pts.data_ptr(), r.data_ptr(), n, n_rand, 2, out.data_ptr(), cnt.data_ptr(), st.data_ptr(),
+                                            scratch.data_ptr(), s))
+        seen.append((st[:2].cpu().numpy().tobytes(), int(cnt[0]), out[:int(cnt[0])].cpu()))
+    for b, c, o in seen[1:]:
+        assert b == seen[0][0] and c == seen[0][1] and torch.equal(o, seen[0][2])
+    a = r[:n_rand].abs().double()
+    sums = np.frombuffer(seen[0][0], dtype=np.float64)
+    assert abs(sums[0] - float(a.sum())) <= 1e-10 * float(a.sum()) and abs(sums[1] - float((a * a).sum())) <= 1e-10 * float((a * a).sum())
+    _cut, want = O.targeted_cutoff_select(pts.cpu(), r.cpu(), n_rand)
+    assert torch.equal(seen[0][2], want)
+    assert torch.equal(P.Update_Targeted_Points(pts, r, n_rand).cpu(), want)
+
+
+def test_philox_known_answers_through_c_abi():
+    """Random123's known-answer vectors for philox4x32 (10 rounds) through the library's raw entry point (bit-exact integer work),
+    and the same block function seen through pdl_sample_points at counter 0 / key 0."""
+    from pde_learn_b200 import _lib as L
+    import pde_learn_b200 as P
+    rows = [list(c) + list(k) for c, k, _ in O.PHILOX_KAT]
+    inp = torch.tensor(np.array(rows, dtype=np.uint32).view(np.int32), device=_dev())
+    out = torch.zeros((len(rows), 4), dtype=torch.int32, device=_dev())
+    L.check(L.lib().pdl_philox4x32_10_raw(inp.data_ptr(), len(rows), out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    got = out.cpu().numpy().view(np.uint32)
+    for i, (_c, _k, want) in enumerate(O.PHILOX_KAT):
+        assert tuple(int(v) for v in got[i]) == want, (i, [hex(int(v)) for v in got[i]])
+    # counter 0, key 0 -> words 6627e8d5 e169c58d ...: on [0, 1) x [0, 1) the sampler returns (word >> 8) * 2^-24
+    p = P.Generate_Points(np.array([[0.0, 1.0], [0.0, 1.0]]), 1, _dev(), Seed=0, First_Index=0).cpu().numpy()[0]
+    assert p[0] == np.float32((0x6627e8d5 >> 8) * 2.0 ** -24) and p[1] == np.float32((0xe169c58d >> 8) * 2.0 ** -24)
+    # a large block of counters against the numpy restatement
+    n = 4096
+    rng = np.random.default_rng(0)
+    ck = rng.integers(0, 2 ** 32, size=(n, 6), dtype=np.uint64).astype(np.uint32)
+    inp = torch.tensor(ck.view(np.int32), device=_dev())
+    out = torch.zeros((n, 4), dtype=torch.int32, device=_dev())
+    L.check(L.lib().pdl_philox4x32_10_raw(inp.data_ptr(), n, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), O.philox4x32_10(ck[:, :4], ck[:, 4:]))
+
+
+@pytest.mark.parametrize("first", [0, 12345, (1 << 32) - 7])
+def test_sampler_matches_oracle_restatement(first):
+    """pdl_sample_points against oracle.sample_points (Philox words -> coordinates), incl. a shard offset that crosses 2^32."""
+    import pde_learn_b200 as P
+    bounds = np.array([[0.0, 50.0], [-10.0, 10.0], [-3.0, 7.5]])
+    n, seed = 5000, 0x1234567_89ABCDEF
+    got = P.Generate_Points(bounds, n, _dev(), Seed=seed, First_Index=first).cpu().numpy()
+    want = O.sample_points(bounds, n, seed, first)
+    assert got.shape == want.shape
+    ulp = np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64))
+    assert ulp.max() <= 1 and (ulp != 0).mean() < 1e-3          # float64 emulation of the fused multiply-add may double-round
+    assert (got >= bounds[:, 0].astype(np.float32)).all() and (got <= bounds[:, 1].astype(np.float32)).all()
 
 
 def test_adam_matches_torch():
@@ -507,8 +574,7 @@ VARIANT_CODE = (
 
 # the non-default code paths of the tensor-pipe engine (the plan compiler's defaults are covered by every other test):
 # plain 3xTF32 everywhere, the other order of the hidden-layer adjoint for both fixtures, bf16 cross terms in the forward pass too
-KERNEL_VARIANTS = [({"PDL_CROSS_BF16": "0"}, 1e-5), ({"PDL_ADJ_FUSED": "1"}, 1e-5), ({"PDL_ADJ_FUSED": "0"}, 1e-5),
-                   ({"PDL_CROSS_BF16": "7"}, 3e-5)]
+from tests.fixtures_meta import KERNEL_VARIANTS      # plain data shared with __graft_entry__.build()
 
 
 @pytest.mark.parametrize("env,tol", KERNEL_VARIANTS)

@@ -167,3 +167,19 @@ def test_targeted_cutoff_select():
     a = r.abs()
     assert abs(cutoff - float(a[:200].mean() + 3 * a[:200].std())) < 1e-6
     assert sel.shape[0] == int((a >= cutoff).sum()) and sel.shape[0] >= 2
+
+
+def test_philox_oracle_known_answers():
+    """The sampler's block function (oracle restatement) against Random123's published known-answer vectors."""
+    for c, k, want in O.PHILOX_KAT:
+        got = O.philox4x32_10(np.array([c], dtype=np.uint32), np.array([k], dtype=np.uint32))[0]
+        assert tuple(int(v) for v in got) == want
+
+
+def test_sampler_oracle_properties():
+    b = [(0.0, 10.0), (-8.0, 8.0)]
+    a = O.sample_points(b, 4096, seed=7, first_index=0)
+    s = O.sample_points(b, 1024, seed=7, first_index=1024)
+    assert np.array_equal(a[1024:2048], s)                      # a shard is a slice of the global batch
+    assert a.dtype == np.float32 and (a[:, 0] >= 0).all() and (a[:, 0] <= 10).all() and (a[:, 1] >= -8).all() and (a[:, 1] <= 8).all()
+    assert abs(a[:, 0].mean() - 5.0) < 0.2 and abs(a[:, 1].mean()) < 0.3
