@@ -32,9 +32,14 @@ using namespace pdl;
 #ifndef PDL_TC_NWG
 #define PDL_TC_NWG 2
 #endif
-#ifndef PDL_TC_ROUND_LO
-#define PDL_TC_ROUND_LO 1      // 1: lo = TF32_rna(x - hi) like the mma.sync forward; 0: raw (the tensor core truncates it)
+#ifndef PDL_TC_SPLIT
+#define PDL_TC_SPLIT 2
 #endif
+// how an activation x becomes the two TF32 operands (the tensor core reads the upper 19 bits of a 32-bit operand, i.e. it truncates):
+//   0: hi = rna(x), lo = rna(x - hi)      5 instructions per value (what the mma.sync forward does)
+//   1: hi = rna(x), lo = x - hi (raw)     3
+//   2: hi = x (raw), lo = x - trunc(x)    2   -- all three are at FP32-matmul level in a 4-layer tanh chain (8e-7 .. 9.7e-7 relative,
+//                                               plain FP32 matmul 7.4e-7 .. 8.1e-7: numpy emulation) and in the parity tests
 constexpr int NWG = PDL_TC_NWG;                    // activation warpgroups
 constexpr int NACT = 4 * NWG;                      // activation warps; warp NACT is the issuer
 constexpr int THREADS = 32 * (NACT + 1);
@@ -50,7 +55,7 @@ static_assert(H >= 2, "needs a hidden->hidden layer");
 constexpr uint32_t TM_D0 = 0, TM_D1 = DCOLS, TM_A = 2 * DCOLS;
 constexpr int NMM = H - 1;                         // tensor-core layers per tile
 constexpr int NPW = 8 / NWG;                       // neurons of a k-step per warpgroup
-static_assert(NWG == 1 || NWG == 2, "1 or 2 activation warpgroups");
+static_assert(NWG == 1 || NWG == 2 || NWG == 4, "1, 2 or 4 activation warpgroups");
 
 struct Smem {
     float B[NMM][2][WP / 4][NP][4];                // [layer][hi/lo][k chunk][n][4]: K-major, 8 x 16-byte core matrices
@@ -61,7 +66,7 @@ struct Smem {
     float rat[H][8];
     float xi[KX];
     float bH;
-    float upart[2][128][J];                        // partial output sums of warpgroup 1, double buffered by tile parity
+    float upart[2][NWG > 1 ? NWG - 1 : 1][128][J]; // partial output sums of warpgroups 1.., double buffered by tile parity
     double red[2][4];
     unsigned long long a_full[2], a_empty[2], d_full[2];
     uint32_t tmem_base;
@@ -94,6 +99,13 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(s32(bar)) : "memory");
 }
+#ifdef PDL_TC_PROFILE
+#define TC_T0() const long long t0_ = clock64()
+#define TC_ACC(x) (x) += clock64() - t0_
+#else
+#define TC_T0() do {} while (0)
+#define TC_ACC(x) do {} while (0)
+#endif
 // bounded wait: a wrong barrier protocol must end in an error, not in a hung GPU
 __device__ __forceinline__ bool mbar_wait(unsigned long long* bar, uint32_t parity, volatile int* failed) {
     const uint32_t a = s32(bar);
@@ -130,12 +142,23 @@ __device__ __forceinline__ void tm_st8(uint32_t taddr, const uint32_t (&r)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
                  "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
+__device__ __forceinline__ void tm_ld2(uint32_t taddr, float (&v)[2]) {
+    uint32_t r[2];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];\n" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr));
+    v[0] = __uint_as_float(r[0]); v[1] = __uint_as_float(r[1]);
+}
+__device__ __forceinline__ void tm_st2(uint32_t taddr, const uint32_t (&r)[2]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};\n" ::"r"(taddr), "r"(r[0]), "r"(r[1]) : "memory");
+}
 template <int N> __device__ __forceinline__ void tm_ldn(uint32_t taddr, float (&v)[N]);
+template <> __device__ __forceinline__ void tm_ldn<2>(uint32_t taddr, float (&v)[2]) { tm_ld2(taddr, v); }
+
 template <> __device__ __forceinline__ void tm_ldn<8>(uint32_t taddr, float (&v)[8]) { tm_ld8(taddr, v); }
 template <> __device__ __forceinline__ void tm_ldn<4>(uint32_t taddr, float (&v)[4]) { tm_ld4(taddr, v); }
 template <int N> __device__ __forceinline__ void tm_stn(uint32_t taddr, const uint32_t (&r)[N]);
 template <> __device__ __forceinline__ void tm_stn<8>(uint32_t taddr, const uint32_t (&r)[8]) { tm_st8(taddr, r); }
 template <> __device__ __forceinline__ void tm_stn<4>(uint32_t taddr, const uint32_t (&r)[4]) { tm_st4(taddr, r); }
+template <> __device__ __forceinline__ void tm_stn<2>(uint32_t taddr, const uint32_t (&r)[2]) { tm_st2(taddr, r); }
 __device__ __forceinline__ void tm_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void tm_st16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(taddr),
@@ -182,9 +205,10 @@ __device__ __forceinline__ int slot_of(long long gg) { return (int)(gg % NSLOT);
 __device__ __forceinline__ uint32_t use_of(long long gg) { return (uint32_t)(gg / NSLOT); }
 
 // activation warps: jets h of this warpgroup's NPW neurons -> hi/lo TF32 -> ring slot of k-step gg
-__device__ __forceinline__ void produce(Smem& S, uint32_t lane_addr, long long gg, int wg, const float (&h)[NPW][J], int lane) {
+__device__ __forceinline__ void produce(Smem& S, uint32_t lane_addr, long long gg, int wg, const float (&h)[NPW][J], int lane,
+                                        long long& t_wait) {
     const int slot = slot_of(gg);
-    mbar_wait(&S.a_empty[slot], (use_of(gg) & 1u) ^ 1u, &S.failed);        // consumed by the MMAs of its previous use
+    { TC_T0(); mbar_wait(&S.a_empty[slot], (use_of(gg) & 1u) ^ 1u, &S.failed); TC_ACC(t_wait); }   // consumed by the MMAs of its previous use
     fence_after();
     const uint32_t a_out = lane_addr + TM_A + slot * SLOT + wg * NPW;
 #pragma unroll
@@ -192,9 +216,15 @@ __device__ __forceinline__ void produce(Smem& S, uint32_t lane_addr, long long g
         uint32_t whi[NPW], wlo[NPW];
 #pragma unroll
         for (int i = 0; i < NPW; ++i) {
-            whi[i] = tf32_rna(h[i][c]);
-            const float lo = h[i][c] - u2f(whi[i]);
-            wlo[i] = PDL_TC_ROUND_LO ? tf32_rna(lo) : f2u(lo);
+            const float x = h[i][c];
+            if (PDL_TC_SPLIT == 2) {
+                whi[i] = f2u(x);
+                wlo[i] = f2u(x - u2f(f2u(x) & 0xFFFFE000u));
+            } else {
+                whi[i] = tf32_rna(x);
+                const float lo = x - u2f(whi[i]);
+                wlo[i] = (PDL_TC_SPLIT == 0) ? tf32_rna(lo) : f2u(lo);
+            }
         }
         tm_stn<NPW>(a_out + 16 * c, whi);
         tm_stn<NPW>(a_out + 16 * c + 8, wlo);
@@ -208,7 +238,7 @@ __device__ __forceinline__ void produce(Smem& S, uint32_t lane_addr, long long g
 // issuer warp: the NMM tensor-core layers of one tile.  MPAR = parity of the tile's first layer index, so that every TMEM address
 // and shared-memory descriptor offset is a compile-time constant (uniform registers, no per-MMA register shuffling).
 template <int MPAR>
-__device__ __forceinline__ bool issue_tile(Smem& S, long long m0, uint32_t b_base) {
+__device__ __forceinline__ bool issue_tile(Smem& S, long long m0, uint32_t b_base, long long& t_wait) {
 #pragma unroll
     for (int l = 0; l < NMM; ++l) {
         const long long m = m0 + l;
@@ -218,7 +248,7 @@ __device__ __forceinline__ bool issue_tile(Smem& S, long long m0, uint32_t b_bas
             const long long gg = m * NKS + g;
             // slot: NSLOT == 1 -> 0; NSLOT == 2 -> parity of gg = ((MPAR + l) * NKS + g) & 1 when NKS is odd, g & 1 when NKS is even
             const int slot = (NSLOT == 1) ? 0 : ((((MPAR + l) & 1) * (NKS & 1) + g) & 1);
-            if (!mbar_wait(&S.a_full[slot], use_of(gg) & 1u, &S.failed)) return false;
+            { TC_T0(); if (!mbar_wait(&S.a_full[slot], use_of(gg) & 1u, &S.failed)) return false; TC_ACC(t_wait); }
             fence_after();
             const uint32_t a_in = TM_A + slot * SLOT;
             const uint32_t off = (uint32_t)((((l * 2 + 0) * (WP / 4) + 2 * g) * NP) * 16);
@@ -240,7 +270,9 @@ __device__ __forceinline__ bool issue_tile(Smem& S, long long m0, uint32_t b_bas
 __global__ void __launch_bounds__(THREADS, 1) pdl_fwd_tc_kernel(const Params P) {
     extern __shared__ __align__(128) unsigned char tc_raw[];
     Smem& S = *reinterpret_cast<Smem*>(tc_raw + ((128u - (s32(tc_raw) & 127u)) & 127u));
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // warp index through a shuffle: provably warp-uniform for ptxas, so the role branches below are uniform control flow and the issuer's
+    // addresses / descriptors can live in uniform registers
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     stage(P, S, tid);
     if (tid == 0) {
         S.failed = 0;
@@ -268,6 +300,8 @@ __global__ void __launch_bounds__(THREADS, 1) pdl_fwd_tc_kernel(const Params P) 
         const int wg = warp >> 2, quarter = warp & 3;
         const int row = quarter * 32 + lane;                       // TMEM lane = point within the tile
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        long long t_empty = 0, t_dfull = 0, t_ld = 0, t_bar = 0;
+        const long long t_begin = clock64();
         long long it = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const long long m0 = it * NMM;
@@ -292,7 +326,7 @@ __global__ void __launch_bounds__(THREADS, 1) pdl_fwd_tc_kernel(const Params P) 
                     for (int c = 1; c < J; ++c) z[c] = (pdl_comp_axis(c) >= 0) ? S.W0[n][(pdl_comp_axis(c) >= 0) ? pdl_comp_axis(c) : 0] : 0.f;
                     act_forward(z, S.rat[0], h[i], tc);
                 }
-                produce(S, lane_addr, m0 * NKS + g, wg, h, lane);
+                produce(S, lane_addr, m0 * NKS + g, wg, h, lane, t_empty);
             }
             // ---- hidden layers 2..H: pre-activations come out of the tensor core ----
             float u[J];
@@ -301,7 +335,7 @@ __global__ void __launch_bounds__(THREADS, 1) pdl_fwd_tc_kernel(const Params P) 
 #pragma unroll 1
             for (int l = 1; l < H; ++l) {
                 const long long m = m0 + l - 1;                    // the tensor-core layer that produced z_{l+1}
-                mbar_wait(&S.d_full[m & 1], (uint32_t)((m >> 1) & 1), &S.failed);
+                { TC_T0(); mbar_wait(&S.d_full[m & 1], (uint32_t)((m >> 1) & 1), &S.failed); TC_ACC(t_dfull); }
                 fence_after();
                 const uint32_t d_in = lane_addr + ((m & 1) ? TM_D1 : TM_D0) + wg * NPW;
 #pragma unroll 1
@@ -309,7 +343,7 @@ __global__ void __launch_bounds__(THREADS, 1) pdl_fwd_tc_kernel(const Params P) 
                     float zc[J][NPW];
 #pragma unroll
                     for (int c = 0; c < J; ++c) tm_ldn<NPW>(d_in + PITCH * c + 8 * g, zc[c]);
-                    tm_ld_wait();
+                    { TC_T0(); tm_ld_wait(); TC_ACC(t_ld); }
                     float h[NPW][J];
 #pragma unroll
                     for (int i = 0; i < NPW; ++i) {
@@ -320,7 +354,7 @@ __global__ void __launch_bounds__(THREADS, 1) pdl_fwd_tc_kernel(const Params P) 
                         act_forward(z, S.rat[l], h[i], tc);
                     }
                     if (l < H - 1) {
-                        produce(S, lane_addr, (m + 1) * NKS + g, wg, h, lane);
+                        produce(S, lane_addr, (m + 1) * NKS + g, wg, h, lane, t_empty);
                     } else {
 #pragma unroll
                         for (int i = 0; i < NPW; ++i) {
@@ -332,15 +366,17 @@ __global__ void __launch_bounds__(THREADS, 1) pdl_fwd_tc_kernel(const Params P) 
                 }
             }
             // ---- output layer + library terms + residual (thread-local); warpgroup 1 hands its partial sums to warpgroup 0 ----
-            if (NWG == 2) {
-                if (wg == 1) {
+            if (NWG > 1) {
+                if (wg > 0) {
 #pragma unroll
-                    for (int c = 0; c < J; ++c) S.upart[it & 1][row][c] = u[c];
+                    for (int c = 0; c < J; ++c) S.upart[it & 1][wg - 1][row][c] = u[c];
                 }
-                asm volatile("bar.sync 1, %0;\n" ::"n"(NACT * 32) : "memory");
+                { TC_T0(); asm volatile("bar.sync 1, %0;\n" ::"n"(NACT * 32) : "memory"); TC_ACC(t_bar); }
                 if (wg == 0) {
 #pragma unroll
-                    for (int c = 0; c < J; ++c) u[c] += S.upart[it & 1][row][c];
+                    for (int q = 0; q < NWG - 1; ++q)
+#pragma unroll
+                        for (int c = 0; c < J; ++c) u[c] += S.upart[it & 1][q][row][c];
                 }
             }
             if (wg == 0) {
@@ -349,24 +385,36 @@ __global__ void __launch_bounds__(THREADS, 1) pdl_fwd_tc_kernel(const Params P) 
                 pdl_epilogue(u, S.xi, r, du, T);
                 if (valid) {
                     if (P.residual) P.residual[p] = r;
+#ifndef PDL_TC_PROFILE
                     if (P.features) {
 #pragma unroll
                         for (int c = 0; c < J; ++c) P.features[(size_t)c * P.n_points + p] = u[c];
                     }
+#endif
                     lsum += (double)r * (double)r;
                     asum += fabs((double)r);
                 }
             }
         }
+#ifdef PDL_TC_PROFILE
+        if (P.features && lane == 0 && (warp == 0 || warp == 4)) {        // cycles: total, waiting for a free ring slot, for D, for tcgen05.ld, at the tile barrier
+            float* o = P.features + blockIdx.x * 16 + (warp ? 8 : 0);
+            o[0] = (float)(clock64() - t_begin); o[1] = (float)t_empty; o[2] = (float)t_dfull; o[3] = (float)t_ld; o[4] = (float)t_bar; o[5] = (float)it;
+        }
+#endif
     } else {
         // ================= issuer warp (all 32 lanes run the loop; elect.sync inside the wrappers) =================
         const uint32_t b_base = s32(&S.B[0][0][0][0][0]);
-        long long it = 0;
+        long long it = 0, t_full = 0;
+        const long long t_begin = clock64();
         bool ok = true;
         for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
             const long long m0 = it * NMM;
-            ok = (m0 & 1) ? issue_tile<1>(S, m0, b_base) : issue_tile<0>(S, m0, b_base);
+            ok = (m0 & 1) ? issue_tile<1>(S, m0, b_base, t_full) : issue_tile<0>(S, m0, b_base, t_full);
         }
+#ifdef PDL_TC_PROFILE
+        if (P.features && lane == 0) { float* o = P.features + blockIdx.x * 16; o[6] = (float)(clock64() - t_begin); o[7] = (float)t_full; }
+#endif
     }
     // ---- CTA tail: loss partials (double), TMEM release ----
     for (int o = 16; o > 0; o >>= 1) { lsum += __shfl_xor_sync(0xffffffffu, lsum, o); asum += __shfl_xor_sync(0xffffffffu, asum, o); }
