@@ -147,3 +147,31 @@ def test_main_driver_burn_in_then_resume(tmp_path):
     # the save file can be read back (and has the reference's keys)
     blob = P.Load_State(str(tmp_path / "Saves" / out2["Save Name"]), torch.device("cuda", 0))
     assert torch.equal(blob["Xi"].detach().cpu(), out2["Xi"]) and len(blob["RHS Terms"]) == 17
+
+
+def test_resume_reference_save_on_gpu():
+    """(f3) A save written by the reference's main.py (tests/golden/make_reference_save.py) is resumed on the B200: network, Xi and
+    Adam moments restored by Load_State, then three Training epochs on the fixture's points.  The reference resumed the same file on
+    the CPU for the same three epochs (Code/main.py:51-57,140-160,232-246 + Test_Train.py:22); Xi, the parameters and the losses
+    must agree."""
+    import pde_learn_b200 as P
+    z = np.load(os.path.join(GOLDEN_DIR, "reference_save_resume.npz"))
+    st = P.Load_State(os.path.join(GOLDEN_DIR, "reference_save_burgers.pt"), _dev())
+    U, Xi = st["U List"][0], st["Xi"]
+    assert Xi.is_cuda and all(q.is_cuda for q in U.parameters())
+    opt = torch.optim.Adam(list(U.parameters()) + [Xi], lr=1e-3)
+    opt.load_state_dict(st["Optimizer State"])
+    Mask = torch.from_numpy(z["mask"].copy())
+    W = {"Data": 1.0, "Coll": 1.0, "Lp": 0.0002, "L2": 0.000005}
+    inputs = torch.from_numpy(z["inputs"].copy()).to(_dev()); targets = torch.from_numpy(z["targets"].copy()).to(_dev())
+    rel = lambda a, b: abs(a - b) / max(abs(b), 1e-30)
+    for e in range(z["points"].shape[0]):
+        pts = torch.from_numpy(z["points"][e].copy()).to(_dev())
+        out = P.Training([U], Xi, Mask, [pts], [inputs], [targets], st["Derivatives"], st["LHS Term"], st["RHS Terms"], 0.1, W, opt)
+        assert rel(out["Coll Losses"][0], float(z["coll"][e])) <= 1e-5 and rel(out["Data Losses"][0], float(z["data"][e])) <= 1e-5
+        assert rel(out["Total Losses"][0], float(z["total"][e])) <= 1e-5
+        dxi = float(np.abs(Xi.detach().cpu().numpy() - z["xi"][e]).max())
+        assert dxi <= 2e-6, (e, dxi)                       # Adam step = 1e-3; identical moments -> identical steps up to fp32 gradient noise
+    flat = torch.cat([q.detach().reshape(-1) for q in U.parameters()]).cpu().numpy()
+    assert float(np.abs(flat - z["params_after"]).max()) <= 2e-5
+    assert float(opt.state_dict()["state"][0]["step"]) == 12 + 3

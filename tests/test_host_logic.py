@@ -187,3 +187,70 @@ def test_dataset_preparation_matches_reference_files(dim, args, tmp_path):
         assert got[k].dtype == want[k].dtype and got[k].shape == want[k].shape, k
         assert np.array_equal(got[k], want[k]), k
     assert Data_Sets.From_MATLAB(os.path.join(gold, "synthetic_%s.mat" % dim), *args, Directory=str(tmp_path), Seed=11) == path
+
+
+def test_reference_written_save_loads():
+    """A save file written by the reference's own main.py (tests/golden/make_reference_save.py; Code/main.py:487-524) is read by
+    Load_State: network values, Xi, library and Adam moments equal what the reference itself sees in that file."""
+    meta = json.load(open(os.path.join(GOLDEN_DIR, "reference_save_burgers.json")))
+    st = P.Load_State(os.path.join(GOLDEN_DIR, "reference_save_burgers.pt"), torch.device("cpu"))
+    U = st["U List"][0]
+    assert list(U.Widths) == meta["widths"] and [U._Get_Activation_String(a) for a in U.Activation_Functions] == meta["activation_types"]
+    X = torch.tensor(meta["probe_inputs"], dtype=torch.float32)
+    assert np.allclose(U(X).detach().double().view(-1).numpy(), np.array(meta["probe_values"]), rtol=0, atol=1e-7)
+    assert np.array_equal(st["Xi"].detach().double().numpy(), np.array(meta["xi"])) and st["Xi"].requires_grad
+    assert [D.Encoding.tolist() for D in st["Derivatives"]] == meta["derivative_encodings"]
+    assert len(st["RHS Terms"]) == meta["num_rhs_terms"] and st["DataSet Names"] == meta["dataset_names"]
+    lhs, rhs = configs.config("burgers")[3:]
+    assert str(st["LHS Term"]) == str(lhs) and [str(t) for t in st["RHS Terms"]] == [str(t) for t in rhs]   # = the shipped Library.txt
+    opt = torch.optim.Adam(list(U.parameters()) + [st["Xi"]], lr=1e-3)
+    opt.load_state_dict(st["Optimizer State"])                               # main.py:232-246
+    assert len(opt.state_dict()["state"]) == meta["num_param_tensors"]
+    assert float(opt.state_dict()["state"][0]["step"]) == meta["adam_step"]
+
+
+def test_repo_written_save_loads_in_reference(tmp_path):
+    """The other direction: a file written by Save_State is opened by the REFERENCE's classes (Network.Set_State, Network.py:258-283;
+    Build_Term_From_State, Term.py:149-177; Derivative) and its optimiser state loads into a torch Adam over the reference network's
+    parameters, as main.py:51-57,140-160,232-246 does.  Needs /root/reference (this container); skipped on the GPU box."""
+    import subprocess
+    import sys
+    if not os.path.isdir("/root/reference/Code"):
+        pytest.skip("the reference tree is not on this machine")
+    torch.manual_seed(5)
+    d, _, derivs, lhs, rhs = configs.config("kdv")
+    U = P.Network([2, 16, 12, 1], "Rational")
+    with torch.no_grad():
+        U.Activation_Functions[1].a.add_(0.01)
+    Xi = torch.randn(len(rhs), requires_grad=True)
+    opt = torch.optim.Adam(list(U.parameters()) + [Xi], lr=1e-3)
+    (U(torch.rand(8, 2)).sum() + Xi.sum()).backward(); opt.step()
+    X = torch.rand(5, 2)
+    path = str(tmp_path / "save")
+    P.Save_State(path, [U], Xi, opt, derivs, lhs, rhs, ["KdV_Sine_N10_P500"])
+    code = """
+import sys, json, numpy, torch
+for p in ("/root/reference/Code", "/root/reference/Code/Classes", "/root/reference/Code/Readers"): sys.path.insert(0, p)
+from Network import Network
+from Term import Build_Term_From_State
+from Derivative import Derivative
+blob = torch.load(sys.argv[1], weights_only=False)
+st = blob["U States"][0]
+U = Network(Widths=st["Widths"], Hidden_Activation=st["Activation Types"][0], Output_Activation=st["Activation Types"][-1])
+U.Set_State(st)
+Xi = blob["Xi"].detach().clone().requires_grad_(True)
+opt = torch.optim.Adam(list(U.parameters()) + [Xi], lr=1e-3); opt.load_state_dict(blob["Optimizer"])
+D = [Derivative(Encoding=e) for e in blob["Derivative Encodings"]]
+T = [Build_Term_From_State(s) for s in blob["RHS Term States"]]; L = Build_Term_From_State(blob["LHS Term State"])
+X = torch.tensor(json.loads(sys.argv[2]), dtype=torch.float32)
+print("OUT " + json.dumps({"u": U(X).detach().double().view(-1).tolist(), "xi": Xi.detach().double().tolist(), "lhs": str(L),
+      "rhs": [str(t) for t in T], "enc": [[int(v) for v in d.Encoding] for d in D], "names": blob["DataSet Names"],
+      "step": float(opt.state_dict()["state"][0]["step"])}))
+"""
+    r = subprocess.run([sys.executable, "-W", "ignore", "-c", code, path, json.dumps(X.tolist())], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    got = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("OUT ")][0][4:])
+    assert np.allclose(np.array(got["u"]), U(X).detach().double().view(-1).numpy(), rtol=0, atol=1e-7)
+    assert np.array_equal(np.array(got["xi"]), Xi.detach().double().numpy())
+    assert got["lhs"] == str(lhs) and got["rhs"] == [str(t) for t in rhs]
+    assert got["enc"] == [[int(v) for v in D.Encoding] for D in derivs] and got["names"] == ["KdV_Sine_N10_P500"] and got["step"] == 1.0
