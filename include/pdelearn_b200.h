@@ -155,6 +155,15 @@ int pdl_targeted_update_dev(const float* points, const float* residual, int64_t 
                             int64_t n_random, int32_t d, float* out_points, int64_t out_capacity, int64_t* out_count,
                             double* stats, int32_t* block_scratch, void* stream);
 
+/* The selection step alone with everything on the device, for captured epochs that run data-parallel: the moments of |r| over the
+ * random rows of ALL ranks arrive as moments_dev = device double[3] {sum |r|, sum r^2, number of random rows} (the caller
+ * all-reduces pdl_abs_residual_moments' output and the row counts), the cutoff mean + 3*std (Code/main.py:369-380) is formed on the
+ * device, and this rank's rows (count in *n_dev) are compacted as in pdl_targeted_update_dev.  stats: device double[4], [2] receives
+ * the cutoff (float), [3] the selected row count before clamping (int64 bit pattern). */
+int pdl_select_targeted_dev(const float* points, const float* residual, int64_t capacity, const int64_t* n_dev, int32_t d,
+                            const double* moments_dev, float* out_points, int64_t out_capacity, int64_t* out_count,
+                            double* stats, int32_t* block_scratch, void* stream);
+
 /* Fused Adam update over a flat parameter vector (torch.optim.Adam semantics, no weight decay / amsgrad):
  * the optimiser step of Code/Test_Train.py:193 for the Adam branch of Code/main.py:232-246. */
 int pdl_adam_step(float* theta, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,

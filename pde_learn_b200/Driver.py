@@ -89,9 +89,9 @@ def Run_Epochs(U_List: List[Network], Xi: torch.Tensor, Mask: torch.Tensor, Inpu
     append last epoch's targeted points, run Training, optionally Testing on fresh points, update the targeted points.
     `Point_Sampler(data_set_index, epoch, n)` may supply the random points (default: on-device Philox sampler).
     Returns the loss histories (numpy arrays, one row per epoch).
-    `Use_CUDA_Graph=True` (Adam, one process, default sampler) replays the whole epoch as one captured CUDA graph
+    `Use_CUDA_Graph=True` (Adam, default sampler) replays the whole epoch as one captured CUDA graph
     (Epoch_Graph.Captured_Epochs): same numbers, no per-epoch host work; epochs are replayed in chunks of 10 unless Testing
-    is requested every epoch.
+    is requested every epoch.  Together with `Process_Group` the graph contains the two NCCL all-reduces of the data-parallel step.
     `Process_Group` (one process per GPU): the epoch's Num_Train_Coll_Points random rows and the data rows are SHARDED -- rank g
     draws global rows [g*n, (g+1)*n) of the same Philox stream (n = Num_Train_Coll_Points / world, which must divide), takes its
     slice of Inputs/Targets, keeps the targeted points of its own shard, and the targeted cutoff uses the all-reduced moments:
@@ -119,18 +119,18 @@ def Run_Epochs(U_List: List[Network], Xi: torch.Tensor, Mask: torch.Tensor, Inpu
     sample = Point_Sampler or (lambda i, e, n: Generate_Points(Bounds_List[i], n, dev, Seed=(Seed * 1000003 + e) * 64 + i,
                                                                First_Index=rank * n))
     if Use_CUDA_Graph:
-        if Point_Sampler is not None or Process_Group is not None:
-            raise ValueError("Use_CUDA_Graph works with the built-in sampler in one process")
+        if Point_Sampler is not None:
+            raise ValueError("Use_CUDA_Graph works with the built-in sampler")
         from .Epoch_Graph import Captured_Epochs
         cap = Captured_Epochs(U_List, Xi, Mask, Inputs_List, Targets_List, Bounds_List, Derivatives, LHS_Term, RHS_Terms, p, Weights,
-                              Optimizer, Num_Train_Coll_Points, Max_Targeted=Max_Targeted, Seed=Seed)
+                              Optimizer, Num_Train_Coll_Points, Max_Targeted=Max_Targeted, Seed=Seed, Process_Group=Process_Group)
         chunk = 1 if Num_Test_Coll_Points > 0 else 10
         e = drained = 0
         while e < Num_Epochs:
             m = min(chunk, Num_Epochs - e)
             cap.run(m)
             if Num_Test_Coll_Points > 0:
-                tp = [sample(i, Num_Epochs + e, Num_Test_Coll_Points).to(dev) for i in range(S)]
+                tp = [sample(i, Num_Epochs + e, n_test_loc).to(dev) for i in range(S)]
                 te = Testing(U_List, Xi, Mask, tp, Test_Inputs_List or Inputs_List, Test_Targets_List or Targets_List, Derivatives,
                              LHS_Term, RHS_Terms, p, Weights)
                 hist["Test Coll"][e] = te["Coll Losses"]; hist["Test Data"][e] = te["Data Losses"]

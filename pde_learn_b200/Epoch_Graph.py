@@ -11,9 +11,17 @@ allocations and 2 host synchronisations.  This is what small batches need (confi
 
 The optimiser stays a torch.optim.Adam: its state tensors (exp_avg, exp_avg_sq) are updated in place by the fused
 kernel and state["step"] is kept in sync, so Optimizer.state_dict() / Save_State keep the reference's format
-(Code/main.py:519).  Restrictions (checked, loud): Adam without weight decay / amsgrad / maximize, one process (no
-Process_Group), at most `Max_Targeted` targeted rows per data set are carried over (the reference has no bound; the
-count actually selected is recorded, and exceeding the capacity raises when the history is read).
+(Code/main.py:519).  Restrictions (checked, loud): Adam without weight decay / amsgrad / maximize, at most `Max_Targeted`
+targeted rows per data set and rank are carried over (the reference has no bound; the count actually selected is recorded,
+and exceeding the capacity raises when the history is read).
+
+Data parallel (`Process_Group`, one process per GPU, NCCL): the graph then holds the whole {sample -> loss -> all-reduce -> Adam}
+step of SURVEY 8(f) rank 2.  Rank g draws rows [g*n, (g+1)*n) of the epoch's Philox stream (n = Num_Train_Coll_Points / world),
+keeps the targeted rows of its own shard, and two collectives are captured per epoch: one of 5 doubles per data set (row count,
+sum r^2, the |r| moments of the random rows, the data-loss partial) and one of the flat gradient buffer [networks | xi].  The local
+means the kernels produce are rescaled by rows_local / rows_global on the device before the gradient all-reduce, the targeted
+cutoff uses the global moments (pdl_select_targeted_dev), and every rank applies the same Adam update: replicas stay identical and
+the numbers equal the one-process run.  `Inputs_List` / `Targets_List` are this rank's shard of the data rows.
 """
 import ctypes as C
 from typing import Dict, List
@@ -29,13 +37,20 @@ class Captured_Epochs:
     def __init__(self, U_List: List, Xi: torch.Tensor, Mask: torch.Tensor, Inputs_List: List[torch.Tensor],
                  Targets_List: List[torch.Tensor], Bounds_List: List[numpy.ndarray], Derivatives: List, LHS_Term, RHS_Terms: List,
                  p: float, Weights: Dict[str, float], Optimizer: torch.optim.Optimizer, Num_Train_Coll_Points: int,
-                 Max_Targeted: int = None, Seed: int = 0, History_Capacity: int = 4096, First_Epoch: int = 0):
+                 Max_Targeted: int = None, Seed: int = 0, History_Capacity: int = 4096, First_Epoch: int = 0, Process_Group=None):
         assert len(U_List) == len(Inputs_List) == len(Targets_List) == len(Bounds_List)
         assert torch.numel(Xi) == len(RHS_Terms)
         assert 0 < p < 2                                                    # Loss.py:279
         if not isinstance(Optimizer, torch.optim.Adam):
             raise TypeError("Captured_Epochs fuses the Adam update; use Run_Epochs/Training for other optimisers")
-        self.S, self.N = len(U_List), int(Num_Train_Coll_Points)
+        self.group, self.rank, self.world = Process_Group, 0, 1
+        if Process_Group is not None:
+            import torch.distributed as dist
+            self.rank, self.world = dist.get_rank(Process_Group), dist.get_world_size(Process_Group)
+            if int(Num_Train_Coll_Points) % self.world:
+                raise ValueError("Num_Train_Coll_Points must be a multiple of the world size (%d)" % self.world)
+        self.S, self.N_global = len(U_List), int(Num_Train_Coll_Points)
+        self.N = self.N_global // self.world                                # random rows this rank draws per epoch
         self.cap_t = int(Max_Targeted) if Max_Targeted is not None else self.N
         self.U_List, self.Xi, self.opt = U_List, Xi, Optimizer
         self.p, self.W = float(p), dict(Weights)
@@ -96,11 +111,24 @@ class Captured_Epochs:
         self.tscratch = [torch.zeros((cap + 1023) // 1024 + 1, dtype=torch.int32, device=dev) for _ in range(S)]
         self.resid = [torch.zeros(cap, dtype=torch.float32, device=dev) for _ in range(S)]
         self.n_scal = [pl.n_param_scalars for pl in self.coll_plans]
-        self.gc = [torch.zeros(n, dtype=torch.float32, device=dev) for n in self.n_scal]
+        # all gradients of an epoch in ONE flat buffer [network 0 | network 1 | ... | xi]: the unit of the gradient all-reduce
+        self.flat = torch.zeros(sum(self.n_scal) + max(K, 1), dtype=torch.float32, device=dev)
+        offs = [0]
+        for n in self.n_scal:
+            offs.append(offs[-1] + n)
+        self.gc = [self.flat[offs[i]:offs[i + 1]] for i in range(S)]
+        self.red = torch.zeros((S, 5), dtype=torch.float64, device=dev)     # per data set: rows, sum r^2, sum |r|, sum r^2 (random rows), data partial
+        self.mom = torch.zeros((S, 3), dtype=torch.float64, device=dev)     # global moments handed to pdl_select_targeted_dev
+        self.n_data = [int(X.shape[0]) for X in self.inputs]
+        if self.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor(self.n_data, dtype=torch.int64, device=dev)
+            dist.all_reduce(t, group=self.group)
+            self.n_data = [int(v) for v in t.tolist()]
         self.gd = [torch.zeros(n, dtype=torch.float32, device=dev) for n in self.n_scal]
         self.g2 = [torch.zeros(n, dtype=torch.float32, device=dev) for n in self.n_scal]
         self.gx = torch.zeros((S, max(K, 1)), dtype=torch.float32, device=dev)
-        self.gxi = torch.zeros(max(K, 1), dtype=torch.float32, device=dev)
+        self.gxi = self.flat[offs[S]:offs[S] + max(K, 1)]
         self.g_lp = torch.zeros(max(K, 1), dtype=torch.float32, device=dev)
         self.lp = torch.zeros(1, dtype=torch.float32, device=dev)
         self.l2 = torch.zeros(S, dtype=torch.float32, device=dev)
@@ -136,28 +164,49 @@ class Captured_Epochs:
 
     def _epoch(self):
         """One epoch, enqueued on the current stream (captured once, replayed afterwards)."""
-        S, N, K, W, d = self.S, self.N, self.K, self.W, self.d
+        S, N, K, W, d, world = self.S, self.N, self.K, self.W, self.d, self.world
         lib = L.lib()
         stream = torch.cuda.current_stream(self.dev).cuda_stream
+        if world > 1:
+            import torch.distributed as dist
         with torch.no_grad():
             L.check(lib.pdl_lp_loss(self.Xi.data_ptr(), self.mask_dev.data_ptr(), K, self.p, self.lp.data_ptr(), self.g_lp.data_ptr(), stream))
             for i in range(S):
-                L.check(lib.pdl_sample_points_dev(self.bounds[i].ctypes.data_as(C.POINTER(C.c_double)), d, N, self.seeds[i].data_ptr(), 0,
-                                                  self.coll[i].data_ptr(), stream))
+                L.check(lib.pdl_sample_points_dev(self.bounds[i].ctypes.data_as(C.POINTER(C.c_double)), d, N, self.seeds[i].data_ptr(),
+                                                  self.rank * N, self.coll[i].data_ptr(), stream))
                 prm = self.params[i]
                 self.coll_plans[i].launch(self.coll[i], prm, self.Xi, self.mask_dev, None, 0.0, True, self.resid[i], None, self.gc[i],
                                           self.gx[i], self.stats_c[i], n_points_dev=self.count[i])
-                self.data_plans[i].launch(self.inputs[i], prm, None, None, self.targets[i], 1.0 / max(int(self.inputs[i].shape[0]), 1),
+                self.data_plans[i].launch(self.inputs[i], prm, None, None, self.targets[i], 1.0 / max(self.n_data[i], 1),
                                           True, None, None, self.gd[i], None, self.stats_d[i])
                 n = len(prm)
                 ptrs = (C.c_void_p * n)(*[q.data_ptr() for q in prm])
                 sizes = (C.c_int32 * n)(*[int(q.numel()) for q in prm])
                 L.check(lib.pdl_l2_squared_loss(ptrs, sizes, n, self.l2[i:i + 1].data_ptr(), self.g2[i].data_ptr(), stream))
+                if world > 1:                                   # this shard's share of the global sums
+                    L.check(lib.pdl_abs_residual_moments(self.resid[i].data_ptr(), N, self.tstats[i].data_ptr(), stream))
+                    self.red[i, 0:1].copy_(self.count[i])
+                    self.red[i, 1:2].copy_(self.stats_c[i, 1:2])
+                    self.red[i, 2:4].copy_(self.tstats[i][0:2])
+                    self.red[i, 4:5].copy_(self.stats_d[i, 0:1])
+            if world > 1:
+                rows_local = torch.cat(self.count).to(torch.float64)
+                dist.all_reduce(self.red, group=self.group)    # collective 1: 5 doubles per data set
+                ratio = (rows_local / self.red[:, 0]).to(torch.float32)      # local mean -> share of the global mean
+                coll, data = self.red[:, 1] / self.red[:, 0], self.red[:, 4]
+                self.mom[:, 0:2].copy_(self.red[:, 2:4]); self.mom[:, 2].fill_(float(self.N_global))
+                self.gx.mul_(ratio.unsqueeze(1))
+            else:
+                coll, data = self.stats_c[:, 0], self.stats_d[:, 0]
+            for i in range(S):
+                if world > 1:
+                    self.gc[i].mul_(ratio[i])
                 L.check(lib.pdl_axpby3(self.gc[i].data_ptr(), self.n_scal[i], self.gc[i].data_ptr(), W["Coll"], self.gd[i].data_ptr(),
-                                       W["Data"], self.g2[i].data_ptr(), W["L2"], stream))
-            torch.add(self.gx.sum(0) * W["Coll"], self.g_lp, alpha=S * W["Lp"], out=self.gxi)
+                                       W["Data"], self.g2[i].data_ptr(), W["L2"] / world, stream))
+            torch.add(self.gx.sum(0) * W["Coll"], self.g_lp, alpha=S * W["Lp"] / world, out=self.gxi)
+            if world > 1:
+                dist.all_reduce(self.flat, group=self.group)   # collective 2: the flat gradient buffer [networks | xi]
             # losses of this epoch (before the update, like Training's return value) -> history row
-            coll, data = self.stats_c[:, 0], self.stats_d[:, 0]
             l2d, lpd = self.l2.to(torch.float64), self.lp.to(torch.float64)
             totals = W["Data"] * data + W["Coll"] * coll + W["Lp"] * lpd + W["L2"] * l2d
             # Adam (Code/Test_Train.py:193)
@@ -166,9 +215,15 @@ class Captured_Epochs:
                 L.check(lib.pdl_adam_step_multi(th, g, m, v, n, k, self.lr, self.b1, self.b2, self.eps, self.step_dev.data_ptr(), stream))
             # targeted points for the next epoch (Code/main.py:365-384)
             for i in range(S):
-                L.check(lib.pdl_targeted_update_dev(self.coll[i].data_ptr(), self.resid[i].data_ptr(), N + self.cap_t,
-                                                    self.count[i].data_ptr(), N, d, self.tbuf[i].data_ptr(), self.cap_t,
-                                                    self.tcount[i].data_ptr(), self.tstats[i].data_ptr(), self.tscratch[i].data_ptr(), stream))
+                if world > 1:
+                    L.check(lib.pdl_select_targeted_dev(self.coll[i].data_ptr(), self.resid[i].data_ptr(), N + self.cap_t,
+                                                        self.count[i].data_ptr(), d, self.mom[i].data_ptr(), self.tbuf[i].data_ptr(),
+                                                        self.cap_t, self.tcount[i].data_ptr(), self.tstats[i].data_ptr(),
+                                                        self.tscratch[i].data_ptr(), stream))
+                else:
+                    L.check(lib.pdl_targeted_update_dev(self.coll[i].data_ptr(), self.resid[i].data_ptr(), N + self.cap_t,
+                                                        self.count[i].data_ptr(), N, d, self.tbuf[i].data_ptr(), self.cap_t,
+                                                        self.tcount[i].data_ptr(), self.tstats[i].data_ptr(), self.tscratch[i].data_ptr(), stream))
                 self.coll[i][N:].copy_(self.tbuf[i])
                 torch.add(self.tcount[i], N, out=self.count[i])
             # rows selected before clamping to the carry-over capacity (stats[3], int64 bit pattern): history() raises when rows were lost
@@ -193,7 +248,10 @@ class Captured_Epochs:
         torch.cuda.synchronize(self.dev)
         self._restore(snap)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # with NCCL collectives inside, other threads of the process (the process group's watchdog) keep making CUDA calls while this
+        # thread captures: only this thread's calls belong to the capture
+        mode = {"capture_error_mode": "thread_local"} if self.world > 1 else {}
+        with torch.cuda.graph(self.graph, **mode):
             self._epoch()
         self._restore(snap)          # capture does not execute, but keep the invariant explicit
         return self

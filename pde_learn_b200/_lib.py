@@ -65,6 +65,8 @@ PROTOTYPES = {
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdl_targeted_update_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                           C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pdl_select_targeted_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdl_adam_step_multi": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                       C.POINTER(C.c_int64), C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double,
                                       C.c_void_p, C.c_void_p]),

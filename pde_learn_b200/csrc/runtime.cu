@@ -402,6 +402,15 @@ __global__ void cutoff_kernel(const double* __restrict__ stats, long long n_rand
     if (var < 0.0) var = 0.0;
     out[0] = (float)(mean + 3.0 * sqrt(var));
 }
+// the same cutoff from moments that live in device memory as three doubles (sum |r|, sum r^2, row count): the all-reduced moments
+// of a batch whose random rows are sharded over ranks (captured multi-process epochs)
+__global__ void cutoff_from_moments_kernel(const double* __restrict__ moments, float* __restrict__ out) {
+    const double n = moments[2];
+    const double mean = n > 0 ? moments[0] / n : 0.0;
+    double var = n > 1 ? (moments[1] - n * mean * mean) / (n - 1.0) : 0.0;
+    if (var < 0.0) var = 0.0;
+    out[0] = (float)(mean + 3.0 * sqrt(var));
+}
 __global__ void select_count_kernel(const float* __restrict__ r, long long n, const long long* __restrict__ n_dev, float cutoff,
                                     const float* __restrict__ cutoff_dev, int* __restrict__ counts) {
     if (cutoff_dev) cutoff = cutoff_dev[0];
@@ -630,6 +639,22 @@ static int targeted_update_impl(const float* points, const float* residual, int6
     select_count_kernel<<<nb, 1024, 0, st>>>(residual, n, (const long long*)n_dev, 0.f, cutoff_dev, block_scratch);
     select_scan_kernel<<<1, 1024, 0, st>>>(block_scratch, nb, (long long*)out_count, out_cap, reinterpret_cast<long long*>(stats + 3));
     select_scatter_kernel<<<nb, 1024, 0, st>>>(points, residual, n, (const long long*)n_dev, d, 0.f, cutoff_dev, block_scratch, out_points, out_cap);
+    PDL_CUDA(cudaGetLastError());
+    return 0;
+}
+int pdl_select_targeted_dev(const float* points, const float* residual, int64_t capacity, const int64_t* n_dev, int32_t d,
+                            const double* moments_dev, float* out_points, int64_t out_capacity, int64_t* out_count, double* stats,
+                            int32_t* block_scratch, void* stream) {
+    if (!n_dev || !moments_dev || !out_count || !block_scratch || !stats || capacity < 0 || out_capacity < 0) return fail("bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (capacity == 0) { PDL_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int64_t), st)); return 0; }
+    float* cutoff_dev = reinterpret_cast<float*>(stats + 2);
+    cutoff_from_moments_kernel<<<1, 1, 0, st>>>(moments_dev, cutoff_dev);
+    const int nb = (int)((capacity + 1023) / 1024);
+    select_count_kernel<<<nb, 1024, 0, st>>>(residual, capacity, (const long long*)n_dev, 0.f, cutoff_dev, block_scratch);
+    select_scan_kernel<<<1, 1024, 0, st>>>(block_scratch, nb, (long long*)out_count, out_capacity, reinterpret_cast<long long*>(stats + 3));
+    select_scatter_kernel<<<nb, 1024, 0, st>>>(points, residual, capacity, (const long long*)n_dev, d, 0.f, cutoff_dev, block_scratch, out_points,
+                                               out_capacity);
     PDL_CUDA(cudaGetLastError());
     return 0;
 }

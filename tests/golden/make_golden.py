@@ -54,10 +54,12 @@ def spec_json(lhs, rhs):
 
 
 def run_case(name, d, lhs, rhs, bounds, hidden, act, n_pts, seed, masked=(), xi_scale=0.1,
-             perturb_rational=False, bias_scale=0.0):
+             perturb_rational=False, bias_scale=0.0, U_trained=None, xi_trained=None):
+    """`U_trained` / `xi_trained` (tests/golden/make_golden_trained.py): a reference network and coefficient vector taken from the end
+    of a reference training run instead of the Xavier initialisation."""
     torch.manual_seed(seed)
     gen = torch.Generator().manual_seed(seed + 1)
-    U = Network(Widths=[d] + list(hidden) + [1], Hidden_Activation=act, Output_Activation="None")
+    U = U_trained if U_trained is not None else Network(Widths=[d] + list(hidden) + [1], Hidden_Activation=act, Output_Activation="None")
     if bias_scale > 0:
         with torch.no_grad():
             for L in U.Layers:
@@ -70,6 +72,8 @@ def run_case(name, d, lhs, rhs, bounds, hidden, act, n_pts, seed, masked=(), xi_
     Derivs, LHS, RHS, encs = ref_terms(lhs, rhs)
     K = len(rhs)
     xi32 = (xi_scale * torch.randn(K, generator=gen)).to(torch.float32)
+    if xi_trained is not None:
+        xi32 = xi_trained.detach().clone().to(torch.float32)
     mask = torch.zeros(K, dtype=torch.bool)
     for k in masked:
         mask[k] = True
@@ -115,12 +119,28 @@ def run_case(name, d, lhs, rhs, bounds, hidden, act, n_pts, seed, masked=(), xi_
         out["grad_%02d" % i] = grads[i].numpy()
         out["dgrad_%02d" % i] = d_grads[i].numpy()
     out["n_params"] = len(params)
+    if U_trained is not None:
+        # conditioning of the case: the error of the reference's OWN float32 path (same functions, float32 network and points)
+        # against its float64 path, as relative max-norms [loss, residual, dtheta, dxi, features]
+        rel = lambda a, b: float(np.max(np.abs(np.asarray(a, dtype=np.float64) - b)) / max(np.max(np.abs(b)), 1e-300))
+        xi_f = xi32.clone().requires_grad_(True)
+        l32, r32 = Coll_Loss(U=U, Xi=xi_f, Mask=mask, Coll_Points=pts32.clone(), Derivatives=Derivs, LHS_Term=LHS, RHS_Terms=RHS)
+        g32 = torch.autograd.grad(l32, list(U.parameters()) + [xi_f], retain_graph=True)
+        P3 = pts32.clone().requires_grad_(True)
+        u3 = U(P3).view(-1)
+        f32 = [Derivative_From_Derivative(Da=D, Db=I, Db_U=u3, Coords=P3).detach().numpy() for D in Derivs]
+        out["ref_fp32_err"] = np.array([
+            abs(float(l32) - float(loss)) / float(loss), rel(r32.detach().numpy(), resid.detach().numpy()),
+            rel(np.concatenate([x.numpy().ravel() for x in g32[:-1]]), np.concatenate([x.numpy().ravel() for x in grads[:-1]])),
+            rel(g32[-1].numpy(), grads[-1].numpy()), max(rel(a, b) for a, b in zip(f32, feats))])
+        print("  reference float32 vs float64 [loss, resid, dtheta, dxi, feats]:", ["%.1e" % v for v in out["ref_fp32_err"]])
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     print("%-22s J=%d K=%d loss=%.6e data=%.6e" % (name, len(encs), K, float(loss), float(d_loss)))
 
 
-def run_training_case(name):
-    """One reference Training() step with Adam + one Testing() call, float32, two data sets sharing xi."""
+def run_training_case(name, optimizer="Adam"):
+    """One reference Training() step with Adam (or LBFGS: one step = up to 20 closure evaluations, Code/main.py:236, README.md:96)
+    + one Testing() call, float32, two data sets sharing xi."""
     d, lhs, rhs, bounds = config_library("heat")
     torch.manual_seed(7)
     gen = torch.Generator().manual_seed(8)
@@ -142,7 +162,8 @@ def run_training_case(name):
         for i, prm in enumerate(U_List[s].parameters()):
             out["p0_%d_%02d" % (s, i)] = prm.detach().numpy().copy()
     params = [q for U in U_List for q in U.parameters()] + [Xi]
-    Opt = torch.optim.Adam(params, lr=1e-3)
+    Opt = torch.optim.Adam(params, lr=1e-3) if optimizer == "Adam" else torch.optim.LBFGS(params, lr=0.1)
+    out["optimizer"] = np.array(optimizer); out["lr"] = 1e-3 if optimizer == "Adam" else 0.1
     test0 = Testing(U_List, Xi, Mask, [c.clone() for c in Coll], Inp, Tgt, Derivs, LHS, RHS, 0.1, W)
     tr = Training(U_List, Xi, Mask, [c.clone() for c in Coll], Inp, Tgt, Derivs, LHS, RHS, 0.1, W, Opt)
     for key in ("Coll Losses", "Data Losses", "L2 Losses", "Total Losses"):
@@ -154,6 +175,10 @@ def run_training_case(name):
         for i, prm in enumerate(U_List[s].parameters()):
             out["p1_%d_%02d" % (s, i)] = prm.detach().numpy().copy()
     out["xi1"] = Xi.detach().numpy().copy()
+    if optimizer != "Adam":                        # losses after the step (LBFGS returns the FIRST closure's losses)
+        test1 = Testing(U_List, Xi, Mask, [c.clone() for c in Coll], Inp, Tgt, Derivs, LHS, RHS, 0.1, W)
+        out["after_Total_Losses"] = np.array(test1["Total Losses"], dtype=np.float64)
+        out["n_iter"] = int(Opt.state[Opt._params[0]]["n_iter"]); out["func_evals"] = int(Opt.state[Opt._params[0]]["func_evals"])
     out["n_params"] = len(list(U_List[0].parameters()))
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     print("%-22s train total=%s" % (name, tr["Total Losses"]))
@@ -196,6 +221,7 @@ if __name__ == "__main__":
              [[((0, 2), 1)], [((0, 0, 2), 1)], [((0, 0, 0, 2), 1)], [((0, 0, 1, 1), 1)], [((0, 0), 2)]],
              [(0.0, 1.0), (-1.0, 1.0), (-1.0, 1.0), (-1.0, 1.0)], [16, 16], "Tanh", 50, 21)
     run_training_case("training_step_heat")
+    run_training_case("training_lbfgs_heat", optimizer="LBFGS")
     run_library_reader_case()
 
 

@@ -91,8 +91,8 @@ numpy.savez("../resume.npz", inputs = inputs.numpy(), targets = targets.numpy(),
 """
 
 
-def main():
-    tmp = tempfile.mkdtemp(prefix="pdl_refsave_")
+def scratch_reference(tmp):
+    """Scratch copy of the reference with the Appendix D shims; returns (root, env)."""
     root = os.path.join(tmp, "ref")
     shutil.copytree(REF, root, symlinks=True)
     os.symlink("Matlab", os.path.join(root, "MATLAB"))
@@ -113,10 +113,14 @@ def main():
     src = open(pts).read()
     fixed = src.replace("random.uniform(Lower_Bound, Upper_Bound)", "random.uniform(float(Lower_Bound), float(Upper_Bound))")
     assert fixed != src, "Points.py:57 not found"
-    src = fixed
-    open(pts, "w").write(src)
+    open(pts, "w").write(fixed)
+    return root, dict(os.environ, PYTHONPATH=stubs, OMP_NUM_THREADS="8")
+
+
+def main():
+    tmp = tempfile.mkdtemp(prefix="pdl_refsave_")
+    root, env = scratch_reference(tmp)
     open(os.path.join(root, "Settings.txt"), "w").write(SETTINGS)
-    env = dict(os.environ, PYTHONPATH=stubs, OMP_NUM_THREADS="8")
     # data set (Data/From_MATLAB.py, Make_Plot off), then the reference's main.py
     mk = ("import numpy, random, torch; numpy.random.seed(0); import From_MATLAB as F; F.Make_Plot = False; "
           "F.From_MATLAB_1D('Burgers_Sine', 0.75, 2000, 500)")

@@ -19,3 +19,16 @@ def test_sharded_training_equals_single_gpu(world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
     assert '"ok": true' in r.stdout, r.stdout[-2000:]
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_captured_epochs_data_parallel(world):
+    """(f2) the captured epoch with the NCCL all-reduces INSIDE the CUDA graph equals the one-process captured run."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(29700 + world), os.path.join(ROOT, "tests", "dist_graph_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+    assert '"ok": true' in r.stdout, r.stdout[-2000:]
+    print(r.stdout[-600:])

@@ -52,19 +52,22 @@ def test_coll_loss_and_gradients_vs_reference_golden(name):
     assert loss.dtype == torch.float32 and loss.dim() == 0 and resid.shape == (pts.shape[0],)
     loss.backward()
     want = float(g.z["coll_loss"])
-    assert abs(float(loss) - want) <= TOL * abs(want)
-    assert rel_max(resid.cpu().numpy(), g.z["residual"]) <= TOL
+    # g.tol(): 1e-5, except for trained cases whose own float32 reference evaluation is further than that from float64
+    assert abs(float(loss) - want) <= g.tol("loss") * abs(want)
+    assert rel_max(resid.cpu().numpy(), g.z["residual"]) <= g.tol("resid")
     got = np.concatenate([p.grad.cpu().numpy().ravel() for p in U.parameters()])
     ref = np.concatenate([x.numpy().ravel() for x in g.grads])
-    assert rel_max(got, ref) <= TOL
-    assert rel_max(xi.grad.cpu().numpy(), g.z["grad_xi"]) <= TOL
+    print("%s: loss %.1e resid %.1e dtheta %.1e dxi %.1e" % (name, abs(float(loss) - want) / abs(want), rel_max(resid.cpu().numpy(), g.z["residual"]),
+                                                           rel_max(got, ref), rel_max(xi.grad.cpu().numpy(), g.z["grad_xi"])))
+    assert rel_max(got, ref) <= g.tol("dtheta")
+    assert rel_max(xi.grad.cpu().numpy(), g.z["grad_xi"]) <= g.tol("dxi")
     for k, m in enumerate(g.mask):
         if m:
             assert float(xi.grad[k]) == 0.0
     # derivative features (the reference's Derivative_From_Derivative outputs)
     feats = P.Evaluate_Derivatives(U, derivs, pts).cpu().numpy()
     for j in range(len(derivs)):
-        assert rel_max(feats[j], g.z["features"][j]) <= TOL, derivs[j]
+        assert rel_max(feats[j], g.z["features"][j]) <= g.tol("feats"), derivs[j]
 
 
 @pytest.mark.parametrize("name", ["burgers_tanh", "heat_rational", "rd2d_tanh", "wave_mixed_tanh", "burgers_rational20"])
@@ -278,6 +281,47 @@ def test_training_step_vs_reference_golden():
             # at 2% of the step size (lr = 1e-3)
             assert float((prm.detach().cpu() - torch.from_numpy(z["p1_%d_%02d" % (i, j)])).abs().max()) <= 2e-5
     assert float((Xi.detach().cpu() - torch.from_numpy(z["xi1"])).abs().max()) <= 2e-5
+    assert float(Xi[3]) == float(z["xi0"][3])          # masked component untouched
+
+
+def test_training_lbfgs_step_vs_reference_golden():
+    """(f2) The reference's other optimiser (Code/main.py:236, README.md:96): one torch.optim.LBFGS step = 20 re-entries of the fused
+    closure (Optimizer.step(Closure), Code/Test_Train.py:193).  Same start as the reference's own LBFGS step
+    (tests/golden/training_lbfgs_heat.npz): same iteration count, same parameters and losses after the step."""
+    import pde_learn_b200 as P
+    z = np.load(os.path.join(GOLDEN_DIR, "training_lbfgs_heat.npz"))
+    assert str(z["optimizer"]) == "LBFGS"
+    s = json.loads(str(z["spec"]))
+    fix = lambda t: [(tuple(e), int(p)) for e, p in t]
+    derivs, lhs, rhs = _terms(P, fix(s["lhs"]), [fix(t) for t in s["rhs"]])
+    U_List = []
+    for i in range(2):
+        U = P.Network([int(w) for w in z["widths"]], "Tanh", Device=_dev())
+        with torch.no_grad():
+            for j, prm in enumerate(U.parameters()):
+                prm.copy_(torch.from_numpy(z["p0_%d_%02d" % (i, j)].copy()).to(_dev()))
+        U_List.append(U)
+    Xi = torch.from_numpy(z["xi0"].copy()).to(_dev()).requires_grad_(True)
+    Mask = torch.from_numpy(z["mask"].copy())
+    W = json.loads(str(z["weights"]))
+    coll = [torch.from_numpy(z["coll_%d" % i].copy()).to(_dev()) for i in range(2)]
+    inp = [torch.from_numpy(z["inp_%d" % i].copy()).to(_dev()) for i in range(2)]
+    tgt = [torch.from_numpy(z["tgt_%d" % i].copy()).to(_dev()) for i in range(2)]
+    params = [q for U in U_List for q in U.parameters()] + [Xi]
+    opt = torch.optim.LBFGS(params, lr=float(z["lr"]))
+    P.Training(U_List, Xi, Mask, coll, inp, tgt, derivs, lhs, rhs, float(z["p"]), W, opt)
+    st = opt.state[opt._params[0]]
+    assert int(st["n_iter"]) == int(z["n_iter"]) and int(st["func_evals"]) == int(z["func_evals"])
+    te = P.Testing(U_List, Xi, Mask, coll, inp, tgt, derivs, lhs, rhs, float(z["p"]), W)
+    assert np.allclose(te["Total Losses"], z["after_Total_Losses"], rtol=1e-4)
+    dmax = 0.0
+    for i in range(2):
+        for j, prm in enumerate(U_List[i].parameters()):
+            dmax = max(dmax, float((prm.detach().cpu() - torch.from_numpy(z["p1_%d_%02d" % (i, j)])).abs().max()))
+    dxi = float((Xi.detach().cpu() - torch.from_numpy(z["xi1"])).abs().max())
+    moved = float(np.abs(z["xi1"] - z["xi0"]).max())
+    print("LBFGS step: max |dtheta| %.2e, max |dxi| %.2e (xi moved %.2e)" % (dmax, dxi, moved))
+    assert dmax <= 2e-4 and dxi <= 2e-4 and moved > 50 * dxi
     assert float(Xi[3]) == float(z["xi0"][3])          # masked component untouched
 
 
