@@ -54,6 +54,15 @@ def parse():
     return ap.parse_args()
 
 
+def kernel_stamp(plan_source):
+    """Identifies the kernel a DRAM-traffic capture belongs to: hash of the generated plan source + the hand-written kernel template
+    + the launch helpers (scripts/record_traffic.py writes it next to the ncu numbers, bench.py reports them only while it matches)."""
+    import hashlib
+    csrc = os.path.join(ROOT, "pde_learn_b200", "csrc")
+    return hashlib.sha1((plan_source + open(os.path.join(csrc, "jet_mlp_kernel_mma.cuh")).read() +
+                         open(os.path.join(csrc, "kernel_params.h")).read()).encode()).hexdigest()[:16]
+
+
 def per_gpu_points(workload, n_gpus, scaling="weak", total_points=0):
     """Rows per GPU and per network."""
     from pde_learn_b200 import configs
@@ -357,10 +366,7 @@ def run_ours(args):
         tf32_peak, tf32_src = 1590.0 / 2.0, "B200_PROFILING.md fallback 1.59 PFLOP/s bf16 / 2 = dense TF32, of fallback"
     # DRAM traffic of this kernel is an ncu number (profiles/traffic.json); it is reported only while the kernel it was captured for
     # is still the one that runs (stamp = hash of the generated plan source + the kernel template).
-    import hashlib
-    csrc = os.path.join(ROOT, "pde_learn_b200", "csrc")
-    stamp = hashlib.sha1((src + open(os.path.join(csrc, "jet_mlp_kernel_mma.cuh")).read() +
-                          open(os.path.join(csrc, "kernel_params.h")).read()).encode()).hexdigest()[:16]
+    stamp = kernel_stamp(src)
     traffic, traffic_note = None, "no ncu capture recorded for this workload"
     try:
         rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("%s_%s" % (w, args.activation))

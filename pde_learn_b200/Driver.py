@@ -144,6 +144,8 @@ def Run_Epochs(U_List: List[Network], Xi: torch.Tensor, Mask: torch.Tensor, Inpu
                     for q in range(e, e + m):
                         On_Epoch(q, hist)
             e += m
+        if Process_Group is not None:
+            cap.close()                  # a live graph holding NCCL kernels would block a later destroy_process_group()
         return hist
     for e in range(Num_Epochs):
         coll = [torch.vstack((sample(i, e, n_loc).to(dev), targeted[i])) for i in range(S)]

@@ -238,6 +238,8 @@ class Captured_Epochs:
         """Warm up (module load, function attributes, workspaces) on a side stream, restore the state, then capture."""
         if self.graph is not None:
             return self
+        if getattr(self, "_closed", False):
+            raise RuntimeError("this Captured_Epochs was closed")
         snap = self._snapshot()
         s = torch.cuda.Stream(self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
@@ -282,6 +284,14 @@ class Captured_Epochs:
         self._done += int(Num_Epochs)
         for q in [q for prm in self.params for q in prm] + [self.Xi]:        # what torch.optim.Adam would hold
             self.opt.state[q]["step"] = torch.tensor(self.step0 + self._done, dtype=torch.float32)
+
+    def close(self) -> None:
+        """Drops the captured graph (state and history stay readable).  With a Process_Group call this -- or let the object go out
+        of scope -- BEFORE torch.distributed.destroy_process_group(): a live graph that contains NCCL kernels keeps the communicator
+        busy and the teardown waits for it forever (observed on B200 with NCCL 2.28)."""
+        torch.cuda.synchronize(self.dev)
+        self.graph = None
+        self._closed = True
 
     def history(self) -> Dict[str, numpy.ndarray]:
         """Losses of the epochs replayed since the last call (one device->host copy; synchronises)."""

@@ -133,7 +133,9 @@ def library_key(Derivatives, LHS_Term, RHS_Terms):
     """Hashable description of the library: distinct encodings + (encoding index, power) lists, LHS first.
     Memoised on the identity of the Derivative/Term objects (the cache entry keeps them alive, so an id cannot be reused):
     the epoch loop passes the same objects every call and rebuilding the key costs ~0.1 ms of host time per closure."""
-    ident = (tuple(map(id, Derivatives)), id(LHS_Term), tuple(map(id, RHS_Terms)))
+    # + a cheap fingerprint of the mutable parts: Term.Append (public API kept from the reference) changes a term in place
+    ident = (tuple(map(id, Derivatives)), id(LHS_Term), tuple(map(id, RHS_Terms)),
+             tuple((T.Num_Sub_Terms, tuple(T.Powers)) for T in (LHS_Term, *RHS_Terms)))
     hit = _KEY_CACHE.get(ident)
     if hit is not None:
         return hit[0]
@@ -169,6 +171,28 @@ def collocation_plan(U, Derivatives, LHS_Term, RHS_Terms) -> Plan:
     if key not in _PLANS:
         _PLANS[key] = Plan(widths[0], widths, act, L.PDL_MODE_COLLOCATION, encs, [list(t) for t in terms])
     return _PLANS[key]
+
+
+def validate_configuration(d: int, Hidden_Widths, Hidden_Activation: str, Derivatives, LHS_Term, RHS_Terms) -> None:
+    """Runs the plan generator (no compiler, no GPU) on an architecture + library and raises ValueError with the kernel family's
+    limit that was hit (hidden width <= 64, <= 12 jet components, derivative order <= 6, d <= 4, tanh or Rational).  The Settings
+    driver calls it before any data is loaded, so an unsupported configuration fails at start-up with an actionable message."""
+    key = Hidden_Activation.strip().lower()
+    if key in ("rat", "rational"):
+        act = L.PDL_ACT_RATIONAL
+    elif key == "tanh":
+        act = L.PDL_ACT_TANH
+    else:
+        raise ValueError("Hidden Activation Function %r: the fused kernels implement Tanh and Rational (the reference's other "
+                         "activations have no jet recurrences here, and there is no CPU fallback)" % Hidden_Activation)
+    encs, terms = _library_key(Derivatives, LHS_Term, RHS_Terms)
+    desc, keep = L.make_desc(int(d), [int(d)] + [int(w) for w in Hidden_Widths] + [1], act, L.PDL_MODE_COLLOCATION, encs,
+                             [list(t) for t in terms])
+    try:
+        L.plan_source(desc)
+    except L.NativeLibraryError as ex:
+        raise ValueError("this architecture / library is outside the kernel family's limits (hidden width <= 64, <= 12 jet "
+                         "components after closing the derivative set downward, derivative order <= 6, 2 <= d <= 4): %s" % ex) from None
 
 
 def data_plan(U) -> Plan:

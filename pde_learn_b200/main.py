@@ -68,6 +68,13 @@ def main(argv=None) -> Dict:
     dev = torch.device("cuda", torch.cuda.current_device())
     torch.manual_seed(args.seed)
 
+    if not (S["Load U"] or S["Load Xi, Library"]):
+        # fail before any data is read when the architecture / library is outside the kernels' limits (d is at least the longest
+        # derivative encoding; the exact d is checked again by the plan itself once the data bounds are known)
+        from .engine import validate_configuration
+        Dv, Lh, Rh = Read_Library(S["Library Path"])
+        validate_configuration(max(2, max(len(D.Encoding) for D in Dv)), S["Hidden Layer Widths"], S["Hidden Activation Function"], Dv, Lh, Rh)
+
     saved = None
     if S["Load U"] or S["Load Xi, Library"] or S["Load Optimizer"]:
         saved = Load_State(os.path.join(saves_dir, S["Load File Name"]), dev)

@@ -86,6 +86,8 @@ def main():
                 P.Run_Epochs(U, xi, mask, X, Y, B, derivs, lhs, rhs, 0.1, W, opt, 200, n_tot, **kw)
             torch.cuda.synchronize(); dist.barrier()
             rates[mode] = 200 / (time.perf_counter() - t0)
+            if mode == "graph":
+                cap.close()                      # a live CUDA graph with captured NCCL kernels blocks destroy_process_group()
         out["config1_epochs_per_s"] = rates
         out["config1_graph_speedup"] = rates["graph"] / rates["eager"]
     if rank == 0:
