@@ -60,6 +60,7 @@ def kernel_stamp(plan_source):
     import hashlib
     csrc = os.path.join(ROOT, "pde_learn_b200", "csrc")
     return hashlib.sha1((plan_source + open(os.path.join(csrc, "jet_mlp_kernel_mma.cuh")).read() +
+                         open(os.path.join(csrc, "jet_common.cuh")).read() +
                          open(os.path.join(csrc, "kernel_params.h")).read()).encode()).hexdigest()[:16]
 
 

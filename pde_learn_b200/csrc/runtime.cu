@@ -137,7 +137,7 @@ int pdl_plan_create(const pdl_plan_desc* desc, pdl_plan** out) {
         const std::string src = pdl_host::generate_plan_source(spec, &meta);
         const std::string cdir = csrc_dir(), pdir = plans_dir();
         const std::string hdr = read_file(cdir + (meta.engine == 1 ? "/jet_mlp_kernel_mma.cuh" : "/jet_mlp_kernel.cuh")) +
-                                read_file(cdir + "/kernel_params.h") + (meta.fwd_tc ? read_file(cdir + "/jet_mlp_fwd_tc.cuh") : std::string());
+                                read_file(cdir + "/jet_common.cuh") + read_file(cdir + "/kernel_params.h") + (meta.fwd_tc ? read_file(cdir + "/jet_mlp_fwd_tc.cuh") : std::string());
         if (hdr.size() < 100) return fail("kernel template not found in " + cdir + " (set PDL_CSRC_DIR)");
         const char* xf = getenv("PDL_NVCC_FLAGS");
         const std::string flags = std::string("-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo ") + (xf ? xf : "");

@@ -28,7 +28,8 @@ class KernelParams(C.Structure):
 
 def build_emu(desc):
     src = L.plan_source(desc)
-    hdr = open(os.path.join(CSRC, "jet_mlp_kernel.cuh")).read() + open(os.path.join(CSRC, "jet_mlp_kernel_mma.cuh")).read()
+    hdr = (open(os.path.join(CSRC, "jet_mlp_kernel.cuh")).read() + open(os.path.join(CSRC, "jet_mlp_kernel_mma.cuh")).read() +
+           open(os.path.join(CSRC, "jet_common.cuh")).read())
     tag = hashlib.sha1((src + hdr).encode()).hexdigest()[:16]
     os.makedirs(EMU_DIR, exist_ok=True)
     so = os.path.join(EMU_DIR, "emu_%s.so" % tag)
