@@ -32,7 +32,7 @@ def key_of(item, extra_flags=""):
     desc, _keep = L.make_desc(*item)
     src = L.plan_source(desc)
     engine1 = "jet_mlp_kernel_mma.cuh" in src
-    hdr = rd("jet_mlp_kernel_mma.cuh" if engine1 else "jet_mlp_kernel.cuh") + rd("kernel_params.h")
+    hdr = rd("jet_mlp_kernel_mma.cuh" if engine1 else "jet_mlp_kernel.cuh") + rd("jet_common.cuh") + rd("kernel_params.h")
     if "#define PDL_FWD_TC 1" in src:
         hdr += rd("jet_mlp_fwd_tc.cuh")
     flags = "-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo " + extra_flags
