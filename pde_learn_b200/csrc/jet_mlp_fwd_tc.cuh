@@ -21,7 +21,8 @@
 //   * 2 warpgroups of activation warps, each taking 4 of the 8 neurons of every k-step of the same 128 points = 2 warps per scheduler.
 // TMEM budget (512 columns): 2 x [J accumulators at a pitch of NP (or WP: the NP - WP padding columns of component a then overlap the
 // first columns of component a+1, which only ever adds the zero rows of W)] + NSLOT x 16J ring columns.  heat (J = 4, w = 40):
-// 2 x 192 + 2 x 64 = 512; J = 5: 2 x 208 + 80 = 496; J = 6 at w = 40 does not fit and keeps the mma.sync forward.
+// 2 x 192 + 2 x 64 = 512; J = 5: 2 x 208 + 80 = 496; J = 6 at w = 40 (KS, rd2d): ONE accumulator set, 248 + 2 x 96 = 440 (the
+// activation warps drain a whole layer into registers at the layer boundary, see DOUBLE_D below).
 #pragma once
 #include <cstddef>
 #if !defined(PDL_EMULATE) && defined(PDL_FWD_TC) && PDL_FWD_TC
@@ -49,10 +50,16 @@ constexpr int SLOT = 16 * J;                       // ring slot: per component 8
 constexpr bool ROOMY = 2 * NP * J + 2 * SLOT <= 512;
 constexpr int PITCH = ROOMY ? NP : WP;             // column pitch of the per-component accumulators
 constexpr int DCOLS = PITCH * (J - 1) + NP;
-constexpr int NSLOT = (2 * DCOLS + 2 * SLOT <= 512) ? 2 : 1;
-static_assert(2 * DCOLS + NSLOT * SLOT <= 512, "jet set does not fit the tensor memory (plan_codegen.cpp must not select this engine)");
+// two accumulator sets when they fit (layer l+1 accumulates while layer l is still being read); otherwise ONE set: the activation
+// warps then read their whole share of a layer into registers before they produce the first k-step of the next layer.  No extra
+// barrier is needed for that: every activation warp takes part in every k-step, so the a_full completion of the next layer's first
+// k-step already implies that all of them have drained the accumulators the first MMA overwrites.
+constexpr bool DOUBLE_D = 2 * DCOLS + SLOT <= 512;
+constexpr int NDSET = DOUBLE_D ? 2 : 1;
+constexpr int NSLOT = (NDSET * DCOLS + 2 * SLOT <= 512) ? 2 : 1;
+static_assert(NDSET * DCOLS + NSLOT * SLOT <= 512, "jet set does not fit the tensor memory (plan_codegen.cpp must not select this engine)");
 static_assert(H >= 2, "needs a hidden->hidden layer");
-constexpr uint32_t TM_D0 = 0, TM_D1 = DCOLS, TM_A = 2 * DCOLS;
+constexpr uint32_t TM_D0 = 0, TM_D1 = DOUBLE_D ? DCOLS : 0, TM_A = NDSET * DCOLS;
 constexpr int NMM = H - 1;                         // tensor-core layers per tile
 constexpr int NPW = 8 / NWG;                       // neurons of a k-step per warpgroup
 static_assert(NWG == 1 || NWG == 2 || NWG == 4, "1, 2 or 4 activation warpgroups");
@@ -267,6 +274,31 @@ __device__ __forceinline__ bool issue_tile(Smem& S, long long m0, uint32_t b_bas
     return true;
 }
 
+// activation warps, hidden layers 2..H: one k-step's share of pre-activations (this warpgroup's NPW neurons, all components) ->
+// jets h -> ring slot of the next tensor-core layer, or -- after the last hidden layer -- the output layer's partial sums
+__device__ __forceinline__ void layer_slice(Smem& S, const float (&zc)[J][NPW], int l, int g, int wg, long long m, uint32_t lane_addr, int lane,
+                                            float (&u)[J], long long& t_empty) {
+    float h[NPW][J];
+#pragma unroll
+    for (int i = 0; i < NPW; ++i) {
+        float z[J], tc;
+#pragma unroll
+        for (int c = 0; c < J; ++c) z[c] = zc[c][i];
+        z[0] += S.bias[l - 1][8 * g + wg * NPW + i];
+        act_forward(z, S.rat[l], h[i], tc);
+    }
+    if (l < H - 1) {
+        produce(S, lane_addr, (m + 1) * NKS + g, wg, h, lane, t_empty);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NPW; ++i) {
+            const float w = S.wH[8 * g + wg * NPW + i];
+#pragma unroll
+            for (int c = 0; c < J; ++c) u[c] += w * h[i][c];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(THREADS, 1) pdl_fwd_tc_kernel(const Params P) {
     extern __shared__ __align__(128) unsigned char tc_raw[];
     Smem& S = *reinterpret_cast<Smem*>(tc_raw + ((128u - (s32(tc_raw) & 127u)) & 127u));
@@ -338,31 +370,25 @@ __global__ void __launch_bounds__(THREADS, 1) pdl_fwd_tc_kernel(const Params P) 
                 { TC_T0(); mbar_wait(&S.d_full[m & 1], (uint32_t)((m >> 1) & 1), &S.failed); TC_ACC(t_dfull); }
                 fence_after();
                 const uint32_t d_in = lane_addr + ((m & 1) ? TM_D1 : TM_D0) + wg * NPW;
+                if (DOUBLE_D) {
 #pragma unroll 1
-                for (int g = 0; g < NKS; ++g) {
-                    float zc[J][NPW];
+                    for (int g = 0; g < NKS; ++g) {
+                        float zc[J][NPW];
 #pragma unroll
-                    for (int c = 0; c < J; ++c) tm_ldn<NPW>(d_in + PITCH * c + 8 * g, zc[c]);
+                        for (int c = 0; c < J; ++c) tm_ldn<NPW>(d_in + PITCH * c + 8 * g, zc[c]);
+                        { TC_T0(); tm_ld_wait(); TC_ACC(t_ld); }
+                        layer_slice(S, zc, l, g, wg, m, lane_addr, lane, u, t_empty);
+                    }
+                } else {
+                    // single accumulator set: drain this thread's whole share of the layer first (fully unrolled: register arrays)
+                    float zall[NKS][J][NPW];
+#pragma unroll
+                    for (int g = 0; g < NKS; ++g)
+#pragma unroll
+                        for (int c = 0; c < J; ++c) tm_ldn<NPW>(d_in + PITCH * c + 8 * g, zall[g][c]);
                     { TC_T0(); tm_ld_wait(); TC_ACC(t_ld); }
-                    float h[NPW][J];
 #pragma unroll
-                    for (int i = 0; i < NPW; ++i) {
-                        float z[J], tc;
-#pragma unroll
-                        for (int c = 0; c < J; ++c) z[c] = zc[c][i];
-                        z[0] += S.bias[l - 1][8 * g + wg * NPW + i];
-                        act_forward(z, S.rat[l], h[i], tc);
-                    }
-                    if (l < H - 1) {
-                        produce(S, lane_addr, (m + 1) * NKS + g, wg, h, lane, t_empty);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < NPW; ++i) {
-                            const float w = S.wH[8 * g + wg * NPW + i];
-#pragma unroll
-                            for (int c = 0; c < J; ++c) u[c] += w * h[i][c];
-                        }
-                    }
+                    for (int g = 0; g < NKS; ++g) layer_slice(S, zall[g], l, g, wg, m, lane_addr, lane, u, t_empty);
                 }
             }
             // ---- output layer + library terms + residual (thread-local); warpgroup 1 hands its partial sums to warpgroup 0 ----

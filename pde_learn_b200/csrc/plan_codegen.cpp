@@ -261,13 +261,15 @@ std::string generate_plan_source(const PlanSpec& spec, PlanMeta* meta_out) {
         if (meta.dgrad_mma == 2 && (meta.cross_bf16 & 2) && smem_floats(meta, nw) * 4 > 227 * 1024) meta.cross_bf16 &= ~3;
     }
     // launches without gradients on the tcgen05 / TMEM forward engine (jet_mlp_fwd_tc.cuh) when the jet set fits the 512 tensor-memory
-    // columns: two accumulator sets (J components at a pitch of NP, or WP with overlapping padding columns) + one or two ring slots
+    // columns: two accumulator sets (J components at a pitch of NP, or WP with overlapping padding columns) + one or two ring slots,
+    // or ONE accumulator set + ring when a thread's share of a layer (WP/8 k-steps x J components x 4 neurons) fits 128 registers
     meta.fwd_tc = 0;
     if (meta.engine == 1 && spec.mode == 0 && H >= 2 && spec.fwd_tc != 0) {
         const int NP = (WP + 15) / 16 * 16, SLOT = 16 * J;
         const bool roomy = 2 * NP * J + 2 * SLOT <= 512;
         const int dcols = (roomy ? NP : WP) * (J - 1) + NP;
         if (2 * dcols + SLOT <= 512) meta.fwd_tc = 1;
+        else if (dcols + SLOT <= 512 && (WP / 8) * J * 4 <= 128) meta.fwd_tc = 1;
     }
     while (nw > 1 && smem_floats(meta, nw) * 4 > 227 * 1024) --nw;
     if (smem_floats(meta, nw) * 4 > 227 * 1024) throw std::runtime_error("plan does not fit in shared memory");
