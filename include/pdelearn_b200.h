@@ -181,6 +181,14 @@ int pdl_adam_step_multi(float* const* theta, const float* const* grad, float* co
 int pdl_axpby3(float* out, int64_t n, const float* a, double wa, const float* b, double wb, const float* c, double wc,
                void* stream);
 
+/* Side effect control.  Adjoint launches of >= 2^15 rows keep their workspace in a persisting-L2 window; for that the first such
+ * launch on a device reserves the device's persisting-L2 set-aside (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, max)), which
+ * every other kernel of the process then sees as a smaller L2.  This call returns the set-aside (limit 0) and resets lines still
+ * marked persisting -- for a host application that is done training and goes on to other GPU work.  Later adjoint launches stay
+ * correct; they run without the window (more DRAM write-back, same numbers) until the process restarts.  PDL_L2_PERSIST=0 in the
+ * environment disables the reservation altogether.  No counterpart in the reference (it has no device-side state). */
+int pdl_release_l2_setaside(void);
+
 /* Register-resident FFMA-chain microbenchmark: measured FP32 peak of the current device in TFLOP/s
  * (the roofline denominator).  Synchronises the stream. */
 int pdl_measure_fp32_peak(double* tflops, void* stream);

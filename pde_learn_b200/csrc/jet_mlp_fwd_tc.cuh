@@ -31,7 +31,7 @@ namespace pdl_tc {
 using namespace pdl;
 
 #ifndef PDL_TC_NWG
-#define PDL_TC_NWG 2
+#define PDL_TC_NWG ((PDL_J >= 5) ? 4 : 2)      // measured (profiles/r02_tc_fwd_j6.txt): 4 warpgroups gain 2-6 % from J = 5 on, nothing at J = 4
 #endif
 #ifndef PDL_TC_SPLIT
 #define PDL_TC_SPLIT 2

@@ -154,9 +154,10 @@ int pdl_plan_create(const pdl_plan_desc* desc, pdl_plan** out) {
         std::lock_guard<std::mutex> lock(mu);
         if (!file_exists(so)) {
             mkdir(pdir.c_str(), 0755);
-            // ranks that start together all miss on the same plan: one of them compiles, the others wait on the directory lock
-            // and find the installed module.  Source, log and module are written under per-process names and renamed into place.
-            const std::string lockp = pdir + "/.lock";
+            // ranks that start together all miss on the same plan: one of them compiles, the others wait on the plan's lock file
+            // and find the installed module (different plans compile side by side: build() uses one process per core).  Source, log
+            // and module are written under per-process names and renamed into place.
+            const std::string lockp = base + ".lock";
             const int lfd = open(lockp.c_str(), O_CREAT | O_RDWR, 0644);
             if (lfd >= 0) flock(lfd, LOCK_EX);
             struct Unlock { int fd; ~Unlock() { if (fd >= 0) { flock(fd, LOCK_UN); close(fd); } } } unlock{lfd};
@@ -667,6 +668,14 @@ int pdl_targeted_update_dev(const float* points, const float* residual, int64_t 
                             void* stream) {
     if (!n_dev) return fail("n_dev is null");
     return targeted_update_impl(points, residual, capacity, n_dev, n_random, d, out_points, out_capacity, out_count, stats, block_scratch, stream);
+}
+
+int pdl_release_l2_setaside(void) {
+    // undo the process-wide side effect of the adjoint launches (kernel_params.h: pdl_l2_window reserves the persisting-L2 set-aside once
+    // per device): hand the whole L2 back to normal caching and drop lines that are still marked persisting
+    PDL_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0));
+    PDL_CUDA(cudaCtxResetPersistingL2Cache());
+    return 0;
 }
 
 int pdl_adam_step(float* theta, const float* grad, float* m, float* v, int64_t n, double lr, double b1, double b2, double eps,

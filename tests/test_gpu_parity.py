@@ -284,6 +284,55 @@ def test_training_step_vs_reference_golden():
     assert float(Xi[3]) == float(z["xi0"][3])          # masked component untouched
 
 
+@pytest.mark.parametrize("workload,act", [("heat", "Tanh"), ("heat", "Rational"), ("kdv", "Tanh"), ("ks", "Tanh"), ("rd2d", "Rational")])
+def test_tcgen05_forward_engine_vs_mma_forward_and_oracle(workload, act):
+    """Launches WITHOUT gradients run on the tcgen05 / TMEM engine (csrc/jet_mlp_fwd_tc.cuh: J = 4 and 5 with two accumulator sets,
+    J = 6 with one), launches WITH gradients on the mma.sync engine: same residual and loss from both on ragged row counts
+    (1 ... 65 537: partial 128-point tiles, fewer tiles than CTAs, several tiles per CTA), features against the float64 oracle."""
+    import pde_learn_b200 as P
+    from pde_learn_b200 import _lib as L
+    from pde_learn_b200 import configs, engine
+    d, bounds, derivs, lhs, rhs = configs.config(workload)
+    torch.manual_seed(3)
+    U = P.Network([d] + [40] * 5 + [1], act, Device=_dev())
+    with torch.no_grad():
+        for l in U.Layers:
+            l.bias.add_(0.1 * torch.randn_like(l.bias))
+    K = len(rhs)
+    xi = (0.1 * torch.randn(K)).to(_dev())
+    mask = torch.zeros(K, dtype=torch.uint8, device=_dev()); mask[1] = 1
+    plan = engine.collocation_plan(U, derivs, lhs, rhs)
+    assert "#define PDL_FWD_TC 1" in L.plan_source(plan.desc)              # the plan compiler picked the tensor-memory forward
+    prm = [q.detach() for q in engine.network_param_tensors(U)]
+    for B in (1, 127, 128, 129, 1000, 18945, 65537):
+        pts = P.Generate_Points(bounds, B, _dev(), Seed=B)
+        r_f = torch.full((B,), 7.0, device=_dev()); r_b = torch.zeros(B, device=_dev())
+        feats = torch.zeros((plan.J, B), device=_dev())
+        st_f = torch.zeros(4, dtype=torch.float64, device=_dev()); st_b = torch.zeros(4, dtype=torch.float64, device=_dev())
+        gp = torch.empty(plan.n_param_scalars, device=_dev()); gx = torch.empty(K, device=_dev())
+        plan.launch(pts, prm, xi, mask, None, 1.0 / B, False, r_f, feats, None, None, st_f)
+        plan.launch(pts, prm, xi, mask, None, 1.0 / B, True, r_b, None, gp, gx, st_b)
+        torch.cuda.synchronize()
+        scale = float(r_b.abs().max())
+        assert float((r_f - r_b).abs().max()) <= TOL * scale, (B, float((r_f - r_b).abs().max()) / scale)
+        assert abs(float(st_f[0]) - float(st_b[0])) <= TOL * abs(float(st_b[0])), B
+        assert abs(float(st_f[2]) - float(st_b[2])) <= TOL * abs(float(st_b[2])), B          # sum |r| (targeted-point moments)
+    # features of the last (largest) launch against the float64 oracle on a subset of its rows
+    n = 400
+    idx = torch.linspace(0, B - 1, n).long().to(_dev())
+    Ws = [l.weight.detach().cpu() for l in U.Layers]; bs = [l.bias.detach().cpu() for l in U.Layers]
+    ra = rb = []
+    if act == "Rational":
+        ra = [a.a.detach().cpu() for a in list(U.Activation_Functions)[:-1]]; rb = [a.b.detach().cpu() for a in list(U.Activation_Functions)[:-1]]
+    net = O.NetParams(Ws, bs, act.lower(), list(ra), list(rb)).to(torch.float64, False)
+    od = O.config_library(workload)[0]
+    X = pts[idx].cpu().double().requires_grad_(True)
+    fe = O.derivative_features(lambda Z: O.mlp_forward(net, Z), X, [j[:od] for j in plan.jets])
+    for c, j in enumerate(plan.jets):
+        ref = fe[tuple(j[:od])].detach()
+        assert float((feats[c][idx].cpu().double() - ref).abs().max() / ref.abs().max()) <= TOL, (c, j)
+
+
 def test_training_lbfgs_step_vs_reference_golden():
     """(f2) The reference's other optimiser (Code/main.py:236, README.md:96): one torch.optim.LBFGS step = 20 re-entries of the fused
     closure (Optimizer.step(Closure), Code/Test_Train.py:193).  Same start as the reference's own LBFGS step
