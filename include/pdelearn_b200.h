@@ -181,6 +181,17 @@ int pdl_adam_step_multi(float* const* theta, const float* const* grad, float* co
 int pdl_axpby3(float* out, int64_t n, const float* a, double wa, const float* b, double wb, const float* c, double wc,
                void* stream);
 
+/* The scalar tail of one closure (Code/Test_Train.py:167-183) in one launch: per network i the total
+ * w_data*Data_i + w_coll*Coll_i + w_lp*Lp + w_l2*L2_i (float64), the vector the training loop reports,
+ * scalars[4S+1] = {Coll_0.., Data_0.., L2_0.., Total_0.., Lp}, *total = sum_i Total_i (float32, the value .backward() is called on) and
+ * -- when grad_xi is not NULL -- the xi gradient  w_coll * sum_i grad_xi_coll[i][:] + lp_grad_scale * grad_xi_lp[:].
+ * stats_coll / stats_data: device double [S][4] as written by pdl_loss_launch ([.][0] = the mean); l2: float[S]; lp: float[1];
+ * grad_xi_coll: float [S][ld_grad_xi].  Pass the weights already divided by the world size where the term is replicated. */
+int pdl_closure_tail(const double* stats_coll, const double* stats_data, const float* l2, const float* lp,
+                     const float* grad_xi_coll, const float* grad_xi_lp, int32_t n_networks, int32_t k, int32_t ld_grad_xi,
+                     double w_data, double w_coll, double w_lp, double w_l2, double lp_grad_scale, double* scalars, float* total,
+                     float* grad_xi, void* stream);
+
 /* Side effect control.  Adjoint launches of >= 2^15 rows keep their workspace in a persisting-L2 window; for that the first such
  * launch on a device reserves the device's persisting-L2 set-aside (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, max)), which
  * every other kernel of the process then sees as a smaller L2.  This call returns the set-aside (limit 0) and resets lines still

@@ -74,6 +74,9 @@ PROTOTYPES = {
                                 C.c_double, C.c_double, C.c_double, C.c_int64, C.c_void_p]),
     "pdl_axpby3": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_double,
                              C.c_void_p]),
+    "pdl_closure_tail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]),
     "pdl_release_l2_setaside": (C.c_int, []),
     "pdl_measure_fp32_peak": (C.c_int, [C.POINTER(C.c_double), C.c_void_p]),
 }

@@ -356,16 +356,6 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
     bool first = true;
 
     for (long long tile = gwarp; tile < n_tiles; tile += n_warps, first = false) {
-#if !defined(PDL_EMULATE) && !defined(PDL_NO_POINT_PREFETCH)
-        // the rows of this warp's NEXT tile (8 points = 32 D bytes, one or two cache lines) into L1 while this tile computes: the loads
-        // at the top of the next iteration then hit instead of paying a DRAM round trip with nothing else in flight
-        if (BWD && lane == 0 && tile + n_warps < n_tiles) {
-            const float* nx = P.points + (tile + n_warps) * 8 * D;
-            const float* last = P.points + NPTS * D - 1;                     // a partial last tile: stay inside the array
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-            if (D == 3) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 8 * D - 1 < last ? nx + 8 * D - 1 : last));
-        }
-#endif
         // ---------------- layer 0 forward ----------------
         PDL_FOR_LANES {
             const int pg = lane >> 2, g4 = lane & 3;

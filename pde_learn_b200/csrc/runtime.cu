@@ -523,6 +523,33 @@ __global__ void axpby3_kernel(float* __restrict__ out, long long n, const float*
     }
 }
 
+// ---- the scalar tail of one closure (Code/Test_Train.py:167-183): per-network totals, the reported loss vector, the summed total and
+// the weighted xi gradient  w_coll * sum_i dColl_i/dxi + lp_scale * dLp/dxi  -- one launch instead of a dozen tensor-library kernels ----
+__global__ void closure_tail_kernel(const double* __restrict__ stats_c, const double* __restrict__ stats_d, const float* __restrict__ l2,
+                                    const float* __restrict__ lp, const float* __restrict__ gx, const float* __restrict__ g_lp, int S, int K,
+                                    int ldk, double w_data, double w_coll, double w_lp, double w_l2, float lp_scale,
+                                    double* __restrict__ scalars, float* __restrict__ total, float* __restrict__ grad_xi) {
+    if (grad_xi) {
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            float s = 0.f;
+            for (int i = 0; i < S; ++i) s += gx[(size_t)i * ldk + k];
+            grad_xi[k] = s * (float)w_coll + lp_scale * g_lp[k];
+        }
+    }
+    if (threadIdx.x == 0) {
+        const double lpd = (double)lp[0];
+        double sum = 0.0;
+        for (int i = 0; i < S; ++i) {
+            const double coll = stats_c[4 * i], data = stats_d[4 * i], l2d = (double)l2[i];
+            const double tot = w_data * data + w_coll * coll + w_lp * lpd + w_l2 * l2d;
+            scalars[i] = coll; scalars[S + i] = data; scalars[2 * S + i] = l2d; scalars[3 * S + i] = tot;
+            sum += tot;
+        }
+        scalars[4 * S] = lpd;
+        total[0] = (float)sum;
+    }
+}
+
 // ---- FP32 peak: 8 independent FFMA chains per thread ----
 __global__ void fp32_peak_kernel(float* out, int iters, float a, float b) {
     float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
@@ -714,6 +741,17 @@ int pdl_axpby3(float* out, int64_t n, const float* a, double wa, const float* b,
     long long blocks = (n + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     axpby3_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(out, n, a, (float)wa, b, (float)wb, c, (float)wc);
+    PDL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int pdl_closure_tail(const double* stats_coll, const double* stats_data, const float* l2, const float* lp, const float* grad_xi_coll,
+                     const float* grad_xi_lp, int32_t n_networks, int32_t k, int32_t ld_grad_xi, double w_data, double w_coll, double w_lp,
+                     double w_l2, double lp_grad_scale, double* scalars, float* total, float* grad_xi, void* stream) {
+    if (!stats_coll || !stats_data || !l2 || !lp || !scalars || !total || n_networks < 1 || k < 0) return fail("bad arguments");
+    if (grad_xi && (!grad_xi_coll || !grad_xi_lp || ld_grad_xi < k)) return fail("bad gradient arguments");
+    closure_tail_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(stats_coll, stats_data, l2, lp, grad_xi_coll, grad_xi_lp, n_networks, k, ld_grad_xi,
+                                                             w_data, w_coll, w_lp, w_l2, (float)lp_grad_scale, scalars, total, grad_xi);
     PDL_CUDA(cudaGetLastError());
     return 0;
 }

@@ -392,18 +392,20 @@ class _ClosureFn(torch.autograd.Function):
                     L.check(lib.pdl_axpby3(gc.data_ptr(), P, gc.data_ptr(), W["Coll"], gd.data_ptr(), W["Data"], g2.data_ptr(),
                                            W["L2"] / world, stream))
                 residuals.append(res)
-        coll, data = stats_c[:, 0], stats_d[:, 0]
-        l2d, lpd = l2.to(torch.float64), lp.to(torch.float64)
-        totals = W["Data"] * data + W["Coll"] * coll + (W["Lp"] / world) * lpd + (W["L2"] / world) * l2d
-        scalars = torch.cat([coll, data, l2d, totals, lpd])
-        if want_grad:
-            torch.add(gx.sum(0)[:K] * W["Coll"], g_lp, alpha=S * W["Lp"] / world, out=flat[goff:goff + K])
+        # scalar tail (totals, reported vector, summed total, weighted xi gradient): one launch
+        scalars = torch.empty(4 * S + 1, dtype=torch.float64, device=dev)
+        total = torch.empty(1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            L.check(lib.pdl_closure_tail(stats_c.data_ptr(), stats_d.data_ptr(), l2.data_ptr(), lp.data_ptr(),
+                                         gx.data_ptr() if want_grad else None, g_lp.data_ptr(), S, K, max(K, 1),
+                                         W["Data"], W["Coll"], W["Lp"] / world, W["L2"] / world, S * W["Lp"] / world, scalars.data_ptr(),
+                                         total.data_ptr(), flat[goff:goff + K].data_ptr() if (want_grad and K > 0) else None, stream))
         ctx.flat, ctx.K, ctx.group = flat, K, spec.group
         ctx.shapes = [q.shape for q in params]
         for r in residuals:
             ctx.mark_non_differentiable(r)
         ctx.mark_non_differentiable(scalars)
-        return (totals.sum().to(torch.float32), scalars, *residuals)
+        return (total[0], scalars, *residuals)
 
     @staticmethod
     def backward(ctx, g_total, _g_scalars, *_g_res):
