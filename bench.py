@@ -327,9 +327,9 @@ def run_ours(args):
     # ---- dominant kernel alone (roofline numerator/denominator) ----
     mask_dev = engine.device_mask(Mask, K, dev)
 
-    def kernel_alone(nets, steps, warmup):
+    def kernel_alone(nets, steps, warmup, bwd=True):
         """Average duration of the collocation fwd+adjoint kernel (+ its tiny reduce) launched on its own: CUDA events on the
-        launching stream, L2 flushed between launches."""
+        launching stream, L2 flushed between launches.  bwd=False: the launch without gradients (Testing / evaluation)."""
         plan_ = engine.collocation_plan(nets[0], derivs, lhs, rhs)
         prm0 = [q.detach() for q in engine.network_param_tensors(nets[0])]
         resid = torch.empty(B, dtype=torch.float32, device=dev)
@@ -341,7 +341,8 @@ def run_ours(args):
             flush.zero_()
             if i >= warmup:
                 kev[i - warmup][0].record()
-            plan_.launch(coll[0], prm0, Xi.detach(), mask_dev, None, 1.0 / n_glob, True, resid, None, gp, gx, stats)
+            plan_.launch(coll[0], prm0, Xi.detach(), mask_dev, None, 1.0 / n_glob, bwd, resid, None, gp if bwd else None,
+                         gx if bwd else None, stats)
             if i >= warmup:
                 kev[i - warmup][1].record()
         torch.cuda.synchronize()
@@ -484,6 +485,16 @@ def run_ours(args):
                     "frac_fp32": r_tf / fp32_peak if fp32_peak > 0 else None,
                     "workload": workload_name(w, "rational")}
 
+    # ---- launches without gradients (Testing, Code/Test_Train.py:205-330; residual evaluation): the tcgen05 / TMEM engine when the
+    # plan has one.  Not part of BASELINE.json's metric (that is the fused fwd+bwd loss); reported because it is the Blackwell-native path.
+    f_steps, f_warm = max(3, args.steps // 2), max(3, args.warmup // 2)
+    _fp, f_ms = kernel_alone(U_List, f_steps, f_warm, bwd=False)
+    f_tf = plan.flops_per_point / 3.0 * B / (f_ms * 1e-3) / 1e12          # forward contraction = one third of F
+    forward_only = {"value": world * B / (f_ms * 1e-3), "unit": "points/s (one network, launch without gradients, kernel alone)",
+                    "kernel_ms": f_ms, "steps": f_steps, "warmup": f_warm,
+                    "engine": "tcgen05/TMEM (pdl_fwd_tc_kernel)" if "#define PDL_FWD_TC 1" in src else "mma.sync (pdl_main_kernel<false>)",
+                    "achieved_tflops": f_tf, "frac": f_tf / (tf32_peak if on_tensor_pipe else fp32_peak)}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -496,7 +507,8 @@ def run_ours(args):
                     "api": "pde_learn_b200.Closure_Loss(...).backward() = the closure of Training() (Code/Test_Train.py:143-188); "
                            "the reference's Training also runs the optimiser and returns the residual on the host, which is not part "
                            "of BASELINE.json's metric"},
-            "gpu_launches": (1 + 6 * S) * args.steps}
+            "gpu_launches": (2 + 6 * S) * args.steps}     # per step: Lp, per network {collocation + reduce, data + reduce, L2, axpby3}, closure tail
+    line["forward_only"] = forward_only
     if rational is not None:
         line["rational"] = rational
     if rank == 0:

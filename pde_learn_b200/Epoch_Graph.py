@@ -134,6 +134,8 @@ class Captured_Epochs:
         self.l2 = torch.zeros(S, dtype=torch.float32, device=dev)
         self.stats_c = torch.zeros((S, 4), dtype=torch.float64, device=dev)
         self.stats_d = torch.zeros((S, 4), dtype=torch.float64, device=dev)
+        self.scal = torch.zeros(4 * S + 1, dtype=torch.float64, device=dev)   # pdl_closure_tail: coll_*, data_*, l2_*, total_*, lp
+        self.total32 = torch.zeros(1, dtype=torch.float32, device=dev)
         self.hcap = int(History_Capacity)
         self.hist = torch.zeros((self.hcap, 5 * S + 1), dtype=torch.float64, device=dev)   # coll, data, l2, total, n_targeted | lp
         self._read = 0                                                       # epochs already returned by history()
@@ -203,12 +205,19 @@ class Captured_Epochs:
                     self.gc[i].mul_(ratio[i])
                 L.check(lib.pdl_axpby3(self.gc[i].data_ptr(), self.n_scal[i], self.gc[i].data_ptr(), W["Coll"], self.gd[i].data_ptr(),
                                        W["Data"], self.g2[i].data_ptr(), W["L2"] / world, stream))
-            torch.add(self.gx.sum(0) * W["Coll"], self.g_lp, alpha=S * W["Lp"] / world, out=self.gxi)
             if world > 1:
+                torch.add(self.gx.sum(0) * W["Coll"], self.g_lp, alpha=S * W["Lp"] / world, out=self.gxi)
                 dist.all_reduce(self.flat, group=self.group)   # collective 2: the flat gradient buffer [networks | xi]
-            # losses of this epoch (before the update, like Training's return value) -> history row
-            l2d, lpd = self.l2.to(torch.float64), self.lp.to(torch.float64)
-            totals = W["Data"] * data + W["Coll"] * coll + W["Lp"] * lpd + W["L2"] * l2d
+                # losses of this epoch (before the update, like Training's return value) -> history row
+                l2d, lpd = self.l2.to(torch.float64), self.lp.to(torch.float64)
+                totals = W["Data"] * data + W["Coll"] * coll + W["Lp"] * lpd + W["L2"] * l2d
+            else:
+                # one launch: weighted xi gradient + the epoch's loss vector [coll_*, data_*, l2_*, total_*, lp]
+                L.check(lib.pdl_closure_tail(self.stats_c.data_ptr(), self.stats_d.data_ptr(), self.l2.data_ptr(), self.lp.data_ptr(),
+                                             self.gx.data_ptr(), self.g_lp.data_ptr(), S, K, max(K, 1), W["Data"], W["Coll"], W["Lp"], W["L2"],
+                                             S * W["Lp"], self.scal.data_ptr(), self.total32.data_ptr(),
+                                             self.gxi.data_ptr() if K > 0 else None, stream))
+                l2d, totals, lpd = self.scal[2 * S:3 * S], self.scal[3 * S:4 * S], self.scal[4 * S:4 * S + 1]
             # Adam (Code/Test_Train.py:193)
             self.step_dev += 1.0
             for th, g, m, v, n, k in self._adam:

@@ -254,3 +254,23 @@ print("OUT " + json.dumps({"u": U(X).detach().double().view(-1).tolist(), "xi": 
     assert np.array_equal(np.array(got["xi"]), Xi.detach().double().numpy())
     assert got["lhs"] == str(lhs) and got["rhs"] == [str(t) for t in rhs]
     assert got["enc"] == [[int(v) for v in D.Encoding] for D in derivs] and got["names"] == ["KdV_Sine_N10_P500"] and got["step"] == 1.0
+
+
+def test_library_key_sees_in_place_term_changes():
+    """Term.Append (public API kept from the reference, Code/Classes/Term.py) changes a term in place: the memoised library key must
+    not keep pointing at the old plan."""
+    d, _, derivs, lhs, rhs = configs.config("heat")
+    rhs = list(rhs)
+    k1 = engine.library_key(derivs, lhs, rhs)
+    assert engine.library_key(derivs, lhs, rhs) is k1                      # memo hit on the same objects
+    rhs[0].Append(derivs[-1], 2)
+    k2 = engine.library_key(derivs, lhs, rhs)
+    assert k2 != k1 and len(k2[1][1]) == len(k1[1][1]) + 1                  # the first RHS term gained a sub-term
+
+
+def test_validate_configuration_reports_kernel_limits():
+    d, _, derivs, lhs, rhs = configs.config("ks")
+    engine.validate_configuration(2, [40] * 5, "Rat", derivs, lhs, rhs)
+    for widths, act in (([80] * 3, "Tanh"), ([20] * 3, "Sigmoid")):
+        with pytest.raises(ValueError):
+            engine.validate_configuration(2, widths, act, derivs, lhs, rhs)
