@@ -47,21 +47,34 @@ constexpr int THREADS = 32 * (NACT + 1);
 constexpr int NP = (WP + 15) / 16 * 16;            // MMA N (M = 128 needs a multiple of 16)
 constexpr int NKS = WP / 8;                        // k-steps per layer
 constexpr int SLOT = 16 * J;                       // ring slot: per component 8 hi + 8 lo columns
-constexpr bool ROOMY = 2 * NP * J + 2 * SLOT <= 512;
-constexpr int PITCH = ROOMY ? NP : WP;             // column pitch of the per-component accumulators
-constexpr int DCOLS = PITCH * (J - 1) + NP;
-// two accumulator sets when they fit (layer l+1 accumulates while layer l is still being read); otherwise ONE set: the activation
-// warps then read their whole share of a layer into registers before they produce the first k-step of the next layer.  No extra
-// barrier is needed for that: every activation warp takes part in every k-step, so the a_full completion of the next layer's first
-// k-step already implies that all of them have drained the accumulators the first MMA overwrites.
-constexpr bool DOUBLE_D = 2 * DCOLS + SLOT <= 512;
-constexpr int NDSET = DOUBLE_D ? 2 : 1;
-constexpr int NSLOT = (NDSET * DCOLS + 2 * SLOT <= 512) ? 2 : 1;
-static_assert(NDSET * DCOLS + NSLOT * SLOT <= 512, "jet set does not fit the tensor memory (plan_codegen.cpp must not select this engine)");
-static_assert(H >= 2, "needs a hidden->hidden layer");
-constexpr uint32_t TM_D0 = 0, TM_D1 = DOUBLE_D ? DCOLS : 0, TM_A = NDSET * DCOLS;
 constexpr int NMM = H - 1;                         // tensor-core layers per tile
 constexpr int NPW = 8 / NWG;                       // neurons of a k-step per warpgroup
+// Two ways to spend the 512 columns.  DOUBLE: two accumulator sets (layer l+1 accumulates while layer l is still being read) + a ring
+// of 1-2 slots.  SINGLE: one accumulator set + a ring of up to 6 slots; the activation warps then read their whole share of a layer
+// (NKS k-steps x J components x NPW neurons) into registers before they produce the first k-step of the next layer.  No extra barrier
+// is needed for that: every activation warp takes part in every k-step, so the a_full completion of the next layer's first k-step
+// already implies that all of them have drained the accumulators the first MMA overwrites.  A layer cannot start before the previous
+// one has completed anyway (its first k-step needs the finished pre-activations), so the second accumulator set only overlapped the
+// remaining tcgen05.ld's with MMAs -- a deep ring that lets the activation warps run a whole layer ahead is worth more (measured,
+// profiles/r02_tc_fwd_ring.txt).  PDL_TC_SINGLE_D = 0 / 1 forces one of them (A/B runs), default: SINGLE when it gives >= 3 slots.
+#ifndef PDL_TC_SINGLE_D
+#define PDL_TC_SINGLE_D -1
+#endif
+constexpr int imin(int a, int b) { return a < b ? a : b; }
+constexpr int PITCH2 = (2 * NP * J + 2 * SLOT <= 512) ? NP : WP;
+constexpr int DC2 = PITCH2 * (J - 1) + NP;
+constexpr int NS2 = (2 * DC2 + SLOT <= 512) ? imin(2, (512 - 2 * DC2) / SLOT) : 0;
+constexpr int PITCH1 = (NP * J + 2 * SLOT <= 512) ? NP : WP;
+constexpr int DC1 = PITCH1 * (J - 1) + NP;
+constexpr int NS1 = (NKS * J * NPW <= 128 && DC1 + SLOT <= 512) ? imin(6, (512 - DC1) / SLOT) : 0;
+constexpr bool DOUBLE_D = (PDL_TC_SINGLE_D == 0 && NS2 > 0) || (PDL_TC_SINGLE_D != 1 && !(NS1 >= 3 || NS2 == 0)) || NS1 == 0;
+constexpr int NDSET = DOUBLE_D ? 2 : 1;
+constexpr int PITCH = DOUBLE_D ? PITCH2 : PITCH1;  // column pitch of the per-component accumulators (WP: the NP - WP padding columns of
+constexpr int DCOLS = DOUBLE_D ? DC2 : DC1;        // component a overlap the first columns of component a+1: only zero rows of W land there)
+constexpr int NSLOT = DOUBLE_D ? NS2 : NS1;
+static_assert(NSLOT >= 1 && NDSET * DCOLS + NSLOT * SLOT <= 512, "jet set does not fit the tensor memory (plan_codegen.cpp must not select this engine)");
+static_assert(H >= 2, "needs a hidden->hidden layer");
+constexpr uint32_t TM_D0 = 0, TM_D1 = DOUBLE_D ? DCOLS : 0, TM_A = NDSET * DCOLS;
 static_assert(NWG == 1 || NWG == 2 || NWG == 4, "1, 2 or 4 activation warpgroups");
 
 struct Smem {
@@ -75,7 +88,7 @@ struct Smem {
     float bH;
     float upart[2][NWG > 1 ? NWG - 1 : 1][128][J]; // partial output sums of warpgroups 1.., double buffered by tile parity
     double red[2][4];
-    unsigned long long a_full[2], a_empty[2], d_full[2];
+    unsigned long long a_full[8], a_empty[8], d_full[2];
     uint32_t tmem_base;
     int failed;
 };
@@ -206,16 +219,19 @@ __device__ void stage(const Params& P, Smem& S, int tid) {
     for (int e = tid; e < K; e += THREADS) S.xi[e] = (P.mask[e] != 0) ? 0.f : P.xi[e];
 }
 
-// ring bookkeeping: k-step gg (global counter) uses slot gg % NSLOT for the (gg / NSLOT)-th time.  Every activation warp takes part in
-// every k-step (its warpgroup's NPW neurons), so a waiter is never more than one phase behind the barrier it waits on.
-__device__ __forceinline__ int slot_of(long long gg) { return (int)(gg % NSLOT); }
-__device__ __forceinline__ uint32_t use_of(long long gg) { return (uint32_t)(gg / NSLOT); }
+// ring bookkeeping: the k-steps of a CTA use the slots round-robin; every role keeps its own (slot, wraps) pair and advances it once
+// per k-step, `wraps` = how often the ring has been filled completely = the use count of the current slot.  Every activation warp
+// takes part in every k-step (its warpgroup's NPW neurons), so a waiter is never more than one phase behind the barrier it waits on.
+struct Ring {
+    int slot; uint32_t wraps;
+    __device__ __forceinline__ void next() { if (++slot == NSLOT) { slot = 0; ++wraps; } }
+};
 
-// activation warps: jets h of this warpgroup's NPW neurons -> hi/lo TF32 -> ring slot of k-step gg
-__device__ __forceinline__ void produce(Smem& S, uint32_t lane_addr, long long gg, int wg, const float (&h)[NPW][J], int lane,
+// activation warps: jets h of this warpgroup's NPW neurons -> hi/lo TF32 -> the next ring slot
+__device__ __forceinline__ void produce(Smem& S, uint32_t lane_addr, Ring& ring, int wg, const float (&h)[NPW][J], int lane,
                                         long long& t_wait) {
-    const int slot = slot_of(gg);
-    { TC_T0(); mbar_wait(&S.a_empty[slot], (use_of(gg) & 1u) ^ 1u, &S.failed); TC_ACC(t_wait); }   // consumed by the MMAs of its previous use
+    const int slot = ring.slot;
+    { TC_T0(); mbar_wait(&S.a_empty[slot], (ring.wraps & 1u) ^ 1u, &S.failed); TC_ACC(t_wait); }   // consumed by the MMAs of its previous use
     fence_after();
     const uint32_t a_out = lane_addr + TM_A + slot * SLOT + wg * NPW;
 #pragma unroll
@@ -240,22 +256,20 @@ __device__ __forceinline__ void produce(Smem& S, uint32_t lane_addr, long long g
     fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&S.a_full[slot]);
+    ring.next();
 }
 
 // issuer warp: the NMM tensor-core layers of one tile.  MPAR = parity of the tile's first layer index, so that every TMEM address
 // and shared-memory descriptor offset is a compile-time constant (uniform registers, no per-MMA register shuffling).
 template <int MPAR>
-__device__ __forceinline__ bool issue_tile(Smem& S, long long m0, uint32_t b_base, long long& t_wait) {
+__device__ __forceinline__ bool issue_tile(Smem& S, long long m0, uint32_t b_base, Ring& ring, long long& t_wait) {
 #pragma unroll
     for (int l = 0; l < NMM; ++l) {
-        const long long m = m0 + l;
         const uint32_t d_out = (((MPAR + l) & 1) ? TM_D1 : TM_D0);
 #pragma unroll
         for (int g = 0; g < NKS; ++g) {
-            const long long gg = m * NKS + g;
-            // slot: NSLOT == 1 -> 0; NSLOT == 2 -> parity of gg = ((MPAR + l) * NKS + g) & 1 when NKS is odd, g & 1 when NKS is even
-            const int slot = (NSLOT == 1) ? 0 : ((((MPAR + l) & 1) * (NKS & 1) + g) & 1);
-            { TC_T0(); if (!mbar_wait(&S.a_full[slot], use_of(gg) & 1u, &S.failed)) return false; TC_ACC(t_wait); }
+            const int slot = ring.slot;            // warp-uniform run-time value: the addresses below stay in uniform registers
+            { TC_T0(); if (!mbar_wait(&S.a_full[slot], ring.wraps & 1u, &S.failed)) return false; TC_ACC(t_wait); }
             fence_after();
             const uint32_t a_in = TM_A + slot * SLOT;
             const uint32_t off = (uint32_t)((((l * 2 + 0) * (WP / 4) + 2 * g) * NP) * 16);
@@ -268,6 +282,7 @@ __device__ __forceinline__ bool issue_tile(Smem& S, long long m0, uint32_t b_bas
                 mma_ts(d_out + PITCH * c, a_in + 16 * c + 8, bhi, 1u);
             }
             commit(&S.a_empty[slot]);
+            ring.next();
         }
         commit(&S.d_full[(MPAR + l) & 1]);
     }
@@ -276,7 +291,7 @@ __device__ __forceinline__ bool issue_tile(Smem& S, long long m0, uint32_t b_bas
 
 // activation warps, hidden layers 2..H: one k-step's share of pre-activations (this warpgroup's NPW neurons, all components) ->
 // jets h -> ring slot of the next tensor-core layer, or -- after the last hidden layer -- the output layer's partial sums
-__device__ __forceinline__ void layer_slice(Smem& S, const float (&zc)[J][NPW], int l, int g, int wg, long long m, uint32_t lane_addr, int lane,
+__device__ __forceinline__ void layer_slice(Smem& S, const float (&zc)[J][NPW], int l, int g, int wg, Ring& ring, uint32_t lane_addr, int lane,
                                             float (&u)[J], long long& t_empty) {
     float h[NPW][J];
 #pragma unroll
@@ -288,7 +303,7 @@ __device__ __forceinline__ void layer_slice(Smem& S, const float (&zc)[J][NPW], 
         act_forward(z, S.rat[l], h[i], tc);
     }
     if (l < H - 1) {
-        produce(S, lane_addr, (m + 1) * NKS + g, wg, h, lane, t_empty);
+        produce(S, lane_addr, ring, wg, h, lane, t_empty);
     } else {
 #pragma unroll
         for (int i = 0; i < NPW; ++i) {
@@ -308,7 +323,8 @@ __global__ void __launch_bounds__(THREADS, 1) pdl_fwd_tc_kernel(const Params P) 
     stage(P, S, tid);
     if (tid == 0) {
         S.failed = 0;
-        for (int s = 0; s < 2; ++s) { mbar_init(&S.a_full[s], NACT); mbar_init(&S.a_empty[s], 1); mbar_init(&S.d_full[s], 1); }
+        for (int s = 0; s < NSLOT; ++s) { mbar_init(&S.a_full[s], NACT); mbar_init(&S.a_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) mbar_init(&S.d_full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == NACT) {
@@ -335,6 +351,7 @@ __global__ void __launch_bounds__(THREADS, 1) pdl_fwd_tc_kernel(const Params P) 
         long long t_empty = 0, t_dfull = 0, t_ld = 0, t_bar = 0;
         const long long t_begin = clock64();
         long long it = 0;
+        Ring ring = {0, 0u};
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const long long m0 = it * NMM;
             const long long p = tile * 128 + row;
@@ -358,7 +375,7 @@ __global__ void __launch_bounds__(THREADS, 1) pdl_fwd_tc_kernel(const Params P) 
                     for (int c = 1; c < J; ++c) z[c] = (pdl_comp_axis(c) >= 0) ? S.W0[n][(pdl_comp_axis(c) >= 0) ? pdl_comp_axis(c) : 0] : 0.f;
                     act_forward(z, S.rat[0], h[i], tc);
                 }
-                produce(S, lane_addr, m0 * NKS + g, wg, h, lane, t_empty);
+                produce(S, lane_addr, ring, wg, h, lane, t_empty);
             }
             // ---- hidden layers 2..H: pre-activations come out of the tensor core ----
             float u[J];
@@ -377,7 +394,7 @@ __global__ void __launch_bounds__(THREADS, 1) pdl_fwd_tc_kernel(const Params P) 
 #pragma unroll
                         for (int c = 0; c < J; ++c) tm_ldn<NPW>(d_in + PITCH * c + 8 * g, zc[c]);
                         { TC_T0(); tm_ld_wait(); TC_ACC(t_ld); }
-                        layer_slice(S, zc, l, g, wg, m, lane_addr, lane, u, t_empty);
+                        layer_slice(S, zc, l, g, wg, ring, lane_addr, lane, u, t_empty);
                     }
                 } else {
                     // single accumulator set: drain this thread's whole share of the layer first (fully unrolled: register arrays)
@@ -388,7 +405,7 @@ __global__ void __launch_bounds__(THREADS, 1) pdl_fwd_tc_kernel(const Params P) 
                         for (int c = 0; c < J; ++c) tm_ldn<NPW>(d_in + PITCH * c + 8 * g, zall[g][c]);
                     { TC_T0(); tm_ld_wait(); TC_ACC(t_ld); }
 #pragma unroll
-                    for (int g = 0; g < NKS; ++g) layer_slice(S, zall[g], l, g, wg, m, lane_addr, lane, u, t_empty);
+                    for (int g = 0; g < NKS; ++g) layer_slice(S, zall[g], l, g, wg, ring, lane_addr, lane, u, t_empty);
                 }
             }
             // ---- output layer + library terms + residual (thread-local); warpgroup 1 hands its partial sums to warpgroup 0 ----
@@ -432,11 +449,12 @@ __global__ void __launch_bounds__(THREADS, 1) pdl_fwd_tc_kernel(const Params P) 
         // ================= issuer warp (all 32 lanes run the loop; elect.sync inside the wrappers) =================
         const uint32_t b_base = s32(&S.B[0][0][0][0][0]);
         long long it = 0, t_full = 0;
+        Ring ring = {0, 0u};
         const long long t_begin = clock64();
         bool ok = true;
         for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
             const long long m0 = it * NMM;
-            ok = (m0 & 1) ? issue_tile<1>(S, m0, b_base, t_full) : issue_tile<0>(S, m0, b_base, t_full);
+            ok = (m0 & 1) ? issue_tile<1>(S, m0, b_base, ring, t_full) : issue_tile<0>(S, m0, b_base, ring, t_full);
         }
 #ifdef PDL_TC_PROFILE
         if (P.features && lane == 0) { float* o = P.features + blockIdx.x * 16; o[6] = (float)(clock64() - t_begin); o[7] = (float)t_full; }
