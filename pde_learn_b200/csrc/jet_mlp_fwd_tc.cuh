@@ -31,7 +31,7 @@ namespace pdl_tc {
 using namespace pdl;
 
 #ifndef PDL_TC_NWG
-#define PDL_TC_NWG ((PDL_J >= 5) ? 4 : 2)      // measured (profiles/r02_tc_fwd_j6.txt): 4 warpgroups gain 2-6 % from J = 5 on, nothing at J = 4
+#define PDL_TC_NWG 4      // measured (profiles/r02_tc_fwd_j6.txt, r02_tc_fwd_ring.txt): 4 warpgroups gain 2-6 % over 2 with the deep ring
 #endif
 #ifndef PDL_TC_SPLIT
 #define PDL_TC_SPLIT 2
@@ -54,9 +54,10 @@ constexpr int NPW = 8 / NWG;                       // neurons of a k-step per wa
 // (NKS k-steps x J components x NPW neurons) into registers before they produce the first k-step of the next layer.  No extra barrier
 // is needed for that: every activation warp takes part in every k-step, so the a_full completion of the next layer's first k-step
 // already implies that all of them have drained the accumulators the first MMA overwrites.  A layer cannot start before the previous
-// one has completed anyway (its first k-step needs the finished pre-activations), so the second accumulator set only overlapped the
-// remaining tcgen05.ld's with MMAs -- a deep ring that lets the activation warps run a whole layer ahead is worth more (measured,
-// profiles/r02_tc_fwd_ring.txt).  PDL_TC_SINGLE_D = 0 / 1 forces one of them (A/B runs), default: SINGLE when it gives >= 3 slots.
+// one has completed anyway (its first k-step needs the finished pre-activations), so the second accumulator set only overlaps the
+// remaining tcgen05.ld's with MMAs.  Measured (profiles/r02_tc_fwd_ring.txt): J = 5, where DOUBLE leaves ONE ring slot, gains 13 % from
+// SINGLE with three; J = 4 is neutral (5 slots vs 2: the chain activation -> MMA tail -> next layer is serial either way) and gains 2-4 %
+// together with 4 warpgroups.  PDL_TC_SINGLE_D = 0 / 1 forces one of them (A/B runs), default: SINGLE when it gives >= 3 slots.
 #ifndef PDL_TC_SINGLE_D
 #define PDL_TC_SINGLE_D -1
 #endif
