@@ -225,12 +225,20 @@ __device__ void stage(const Params& P, Smem& S, int tid) {
 // takes part in every k-step (its warpgroup's NPW neurons), so a waiter is never more than one phase behind the barrier it waits on.
 struct Ring {
     int slot; uint32_t wraps;
+    int pending;                                   // slots written but not yet handed to the issuer (activation warps only)
     __device__ __forceinline__ void next() { if (++slot == NSLOT) { slot = 0; ++wraps; } }
 };
+// k-steps handed to the issuer per tcgen05.wait::st + fence + arrive sequence.  Each hand-off costs an activation warp ~250 cycles
+// whatever it carries (profiles/r02_tc_fwd_cycle_accounting_deep_ring.txt), so with a ring deep enough to keep the issuer fed
+// (at least twice the batch) two k-steps share one.
+#ifndef PDL_TC_BATCH
+#define PDL_TC_BATCH 2
+#endif
+constexpr int BATCH = (PDL_TC_BATCH >= 2 && NSLOT >= 2 * PDL_TC_BATCH) ? PDL_TC_BATCH : 1;
 
 // activation warps: jets h of this warpgroup's NPW neurons -> hi/lo TF32 -> the next ring slot
 __device__ __forceinline__ void produce(Smem& S, uint32_t lane_addr, Ring& ring, int wg, const float (&h)[NPW][J], int lane,
-                                        long long& t_wait) {
+                                        long long& t_wait, bool hand_over) {
     const int slot = ring.slot;
     { TC_T0(); mbar_wait(&S.a_empty[slot], (ring.wraps & 1u) ^ 1u, &S.failed); TC_ACC(t_wait); }   // consumed by the MMAs of its previous use
     fence_after();
@@ -253,11 +261,17 @@ __device__ __forceinline__ void produce(Smem& S, uint32_t lane_addr, Ring& ring,
         tm_stn<NPW>(a_out + 16 * c, whi);
         tm_stn<NPW>(a_out + 16 * c + 8, wlo);
     }
+    ring.next();
+    ++ring.pending;
+    if (!hand_over) return;
     tm_st_wait();
     fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&S.a_full[slot]);
-    ring.next();
+    if (lane == 0) {
+        int sl = ring.slot;
+        for (int q = 0; q < ring.pending; ++q) { sl = (sl == 0) ? NSLOT - 1 : sl - 1; mbar_arrive(&S.a_full[sl]); }
+    }
+    ring.pending = 0;
 }
 
 // issuer warp: the NMM tensor-core layers of one tile.  MPAR = parity of the tile's first layer index, so that every TMEM address
@@ -304,7 +318,7 @@ __device__ __forceinline__ void layer_slice(Smem& S, const float (&zc)[J][NPW], 
         act_forward(z, S.rat[l], h[i], tc);
     }
     if (l < H - 1) {
-        produce(S, lane_addr, ring, wg, h, lane, t_empty);
+        produce(S, lane_addr, ring, wg, h, lane, t_empty, (g % BATCH) == BATCH - 1 || g == NKS - 1);
     } else {
 #pragma unroll
         for (int i = 0; i < NPW; ++i) {
@@ -352,7 +366,7 @@ __global__ void __launch_bounds__(THREADS, 1) pdl_fwd_tc_kernel(const Params P) 
         long long t_empty = 0, t_dfull = 0, t_ld = 0, t_bar = 0;
         const long long t_begin = clock64();
         long long it = 0;
-        Ring ring = {0, 0u};
+        Ring ring = {0, 0u, 0};
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const long long m0 = it * NMM;
             const long long p = tile * 128 + row;
@@ -376,7 +390,7 @@ __global__ void __launch_bounds__(THREADS, 1) pdl_fwd_tc_kernel(const Params P) 
                     for (int c = 1; c < J; ++c) z[c] = (pdl_comp_axis(c) >= 0) ? S.W0[n][(pdl_comp_axis(c) >= 0) ? pdl_comp_axis(c) : 0] : 0.f;
                     act_forward(z, S.rat[0], h[i], tc);
                 }
-                produce(S, lane_addr, ring, wg, h, lane, t_empty);
+                produce(S, lane_addr, ring, wg, h, lane, t_empty, (g % BATCH) == BATCH - 1 || g == NKS - 1);
             }
             // ---- hidden layers 2..H: pre-activations come out of the tensor core ----
             float u[J];
@@ -450,7 +464,7 @@ __global__ void __launch_bounds__(THREADS, 1) pdl_fwd_tc_kernel(const Params P) 
         // ================= issuer warp (all 32 lanes run the loop; elect.sync inside the wrappers) =================
         const uint32_t b_base = s32(&S.B[0][0][0][0][0]);
         long long it = 0, t_full = 0;
-        Ring ring = {0, 0u};
+        Ring ring = {0, 0u, 0};
         const long long t_begin = clock64();
         bool ok = true;
         for (long long tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
