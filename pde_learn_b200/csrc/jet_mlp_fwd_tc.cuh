@@ -228,11 +228,11 @@ struct Ring {
     int pending;                                   // slots written but not yet handed to the issuer (activation warps only)
     __device__ __forceinline__ void next() { if (++slot == NSLOT) { slot = 0; ++wraps; } }
 };
-// k-steps handed to the issuer per tcgen05.wait::st + fence + arrive sequence.  Each hand-off costs an activation warp ~250 cycles
-// whatever it carries (profiles/r02_tc_fwd_cycle_accounting_deep_ring.txt), so with a ring deep enough to keep the issuer fed
-// (at least twice the batch) two k-steps share one.
+// k-steps handed to the issuer per tcgen05.wait::st + fence + arrive sequence.  Sharing one hand-off between two k-steps (needs a ring
+// of at least twice the batch) was measured and is OFF: heat 0.553 -> 0.605 ms (profiles/r02_tc_fwd_batch.txt) -- the MMAs of the
+// first k-step of a pair start later and the layer's MMA tail, which the next layer waits for, moves out by the same amount.
 #ifndef PDL_TC_BATCH
-#define PDL_TC_BATCH 2
+#define PDL_TC_BATCH 1
 #endif
 constexpr int BATCH = (PDL_TC_BATCH >= 2 && NSLOT >= 2 * PDL_TC_BATCH) ? PDL_TC_BATCH : 1;
 
