@@ -678,3 +678,47 @@ def test_tensor_pipe_kernel_variants_subprocess(env, tol):
     import sys
     r = subprocess.run([sys.executable, "-c", VARIANT_CODE, str(tol)], capture_output=True, text=True, env=dict(os.environ, **env), timeout=600)
     assert r.returncode == 0 and "VARIANT_OK" in r.stdout, (env, r.stdout[-2000:], r.stderr[-3000:])
+
+
+def test_closure_tail_and_select_targeted_dev_entries():
+    """The two C-ABI entries added in round 2, called directly: pdl_closure_tail against the tensor arithmetic it replaced
+    (Code/Test_Train.py:167-183) and pdl_select_targeted_dev (device-side global moments) against pdl_targeted_update on one shard."""
+    import ctypes as C
+    from pde_learn_b200 import _lib as L
+    dev = _dev()
+    s = torch.cuda.current_stream().cuda_stream
+    torch.manual_seed(0)
+    S, K = 3, 17
+    sc = torch.rand(S, 4, dtype=torch.float64, device=dev); sd = torch.rand(S, 4, dtype=torch.float64, device=dev)
+    l2 = torch.rand(S, device=dev); lp = torch.rand(1, device=dev)
+    gx = torch.randn(S, K, device=dev); glp = torch.randn(K, device=dev)
+    wD, wC, wLp, wL2, scale = 1.0, 0.7, 2e-4, 5e-6, S * 2e-4
+    scal = torch.zeros(4 * S + 1, dtype=torch.float64, device=dev); tot = torch.zeros(1, device=dev); gxi = torch.zeros(K, device=dev)
+    L.check(L.lib().pdl_closure_tail(sc.data_ptr(), sd.data_ptr(), l2.data_ptr(), lp.data_ptr(), gx.data_ptr(), glp.data_ptr(), S, K, K,
+                                     wD, wC, wLp, wL2, scale, scal.data_ptr(), tot.data_ptr(), gxi.data_ptr(), s))
+    totals = wD * sd[:, 0] + wC * sc[:, 0] + wLp * lp.double() + wL2 * l2.double()
+    want = torch.cat([sc[:, 0], sd[:, 0], l2.double(), totals, lp.double()])
+    assert torch.allclose(scal, want, rtol=1e-14, atol=0)
+    assert abs(float(tot) - float(totals.sum())) <= 1e-6 * float(totals.sum())
+    assert torch.allclose(gxi, gx.sum(0) * wC + scale * glp, rtol=1e-6, atol=1e-7)
+    # selection with the moments in device memory == the all-in-one update when the "global" moments are this shard's own
+    n, n_rand, d = 50_003, 40_000, 2
+    pts = torch.rand(n, d, device=dev); r = torch.randn(n, device=dev) * torch.rand(n, device=dev)
+    out1 = torch.empty_like(pts); c1 = torch.zeros(1, dtype=torch.int64, device=dev); st1 = torch.zeros(4, dtype=torch.float64, device=dev)
+    scr = torch.empty((n + 1023) // 1024 + 1, dtype=torch.int32, device=dev)
+    L.check(L.lib().pdl_targeted_update(pts.data_ptr(), r.data_ptr(), n, n_rand, d, out1.data_ptr(), c1.data_ptr(), st1.data_ptr(), scr.data_ptr(), s))
+    mom = torch.zeros(4, dtype=torch.float64, device=dev)
+    L.check(L.lib().pdl_abs_residual_moments(r.data_ptr(), n_rand, mom.data_ptr(), s))
+    mom3 = torch.stack([mom[0], mom[1], torch.tensor(float(n_rand), dtype=torch.float64, device=dev)])
+    out2 = torch.empty_like(pts); c2 = torch.zeros(1, dtype=torch.int64, device=dev); st2 = torch.zeros(4, dtype=torch.float64, device=dev)
+    cnt = torch.tensor([n], dtype=torch.int64, device=dev)
+    L.check(L.lib().pdl_select_targeted_dev(pts.data_ptr(), r.data_ptr(), n, cnt.data_ptr(), d, mom3.data_ptr(), out2.data_ptr(), n,
+                                            c2.data_ptr(), st2.data_ptr(), scr.data_ptr(), s))
+    k = int(c1)
+    assert k == int(c2) and k > 0 and torch.equal(out1[:k], out2[:k])
+    L.check(L.lib().pdl_release_l2_setaside())                   # returns the persisting-L2 set-aside; launches stay correct afterwards
+    import pde_learn_b200 as P
+    g = GoldenCase("heat_tanh"); U = _network_from_golden(g, P); derivs, lhs, rhs = _terms(P, g.lhs, g.rhs)
+    xi = g.xi.to(dev).requires_grad_(True)
+    loss, _r = P.Coll_Loss(U, xi, torch.tensor(g.mask), g.points.to(dev), derivs, lhs, rhs)
+    assert abs(float(loss) - float(g.z["coll_loss"])) <= TOL * float(g.z["coll_loss"])
