@@ -175,3 +175,49 @@ def test_resume_reference_save_on_gpu():
     flat = torch.cat([q.detach().reshape(-1) for q in U.parameters()]).cpu().numpy()
     assert float(np.abs(flat - z["params_after"]).max()) <= 2e-5
     assert float(opt.state_dict()["state"][0]["step"]) == 12 + 3
+
+
+@pytest.mark.parametrize("optimizer,graph", [("LBFGS", False), ("Adam", True)])
+def test_settings_driver_end_to_end(optimizer, graph, tmp_path):
+    """`python -m pde_learn_b200.main` (the Settings.txt workflow of Code/main.py:35-539) on the data-set file the reference's
+    From_MATLAB wrote (tests/golden/Burgers_Sine_N25_P4000.npz): a short burn-in with the given optimiser, then a second run that
+    loads U, Xi + library and the optimiser state from the first run's save file (README.md:90-94) -- finite decreasing losses, a
+    save file in the reference's format after each run, the resumed run continues the optimiser's step count."""
+    import shutil
+    import pde_learn_b200 as P
+    from pde_learn_b200 import configs
+    from pde_learn_b200 import main as driver
+    root = tmp_path
+    os.makedirs(root / "Data" / "DataSets"); os.makedirs(root / "Saves")
+    shutil.copy(os.path.join(GOLDEN_DIR, "Burgers_Sine_N25_P4000.npz"), root / "Data" / "DataSets")
+    (root / "Library.txt").write_text(configs.SHIPPED_LIBRARY)
+    ref = json.load(open(os.path.join(GOLDEN_DIR, "reference_workflow_burgers.json")))
+    epochs = 6 if optimizer == "LBFGS" else 40
+    lr = "0.05" if optimizer == "LBFGS" else ".001"
+
+    def settings(load, name):
+        t = ref["settings"]["burn_in"].replace("DEVICE", "gpu").replace("<previous save>", name)
+        t = t.replace("Number of Epochs [int]:                          1000", "Number of Epochs [int]:                          %d" % epochs)
+        t = t.replace("Optimizer [Adam, LBFGS]:                         Adam", "Optimizer [Adam, LBFGS]:                         " + optimizer)
+        t = t.replace("Learning Rate [float]:                           .001", "Learning Rate [float]:                           " + lr)
+        if load:
+            t = "\n".join(ln.replace("False", "True") if ln.startswith("Load ") else ln for ln in t.splitlines()) + "\n"
+        return t
+
+    (root / "Settings.txt").write_text(settings(False, "None"))
+    argv = ["--settings", str(root / "Settings.txt"), "--quiet"] + (["--cuda-graph"] if graph else [])
+    r1 = driver.main(argv)
+    h = r1["History"]
+    assert np.isfinite(h["Train Total"]).all() and np.isfinite(h["Test Data"]).all()
+    assert h["Train Data"][-1, 0] < h["Train Data"][0, 0]                        # the data loss goes down during burn-in
+    st = P.Load_State(str(root / "Saves" / r1["Save Name"]), _dev())
+    assert st["DataSet Names"] == ["Burgers_Sine_N25_P4000"] and len(st["RHS Terms"]) == 17
+    text = settings(True, r1["Save Name"])
+    assert text.count("True") >= 4                                               # the three load settings + the mask setting
+    (root / "Settings.txt").write_text(text)
+    r2 = driver.main(argv)
+    assert r2["Save Name"] != r1["Save Name"] and np.isfinite(r2["History"]["Train Total"]).all()
+    assert r2["History"]["Train Data"][0, 0] < h["Train Data"][0, 0]              # resumed from the trained state, not from scratch
+    if optimizer == "Adam":
+        blob = torch.load(str(root / "Saves" / r2["Save Name"]), weights_only=False)
+        assert float(blob["Optimizer"]["state"][0]["step"]) == 2 * epochs
