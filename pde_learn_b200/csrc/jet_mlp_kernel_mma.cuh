@@ -26,7 +26,10 @@ constexpr bool DGRAD_T = (PDL_DGRAD_MMA == 1);     // ... with its B fragments f
 // bf16(W), slots 8-15 carry bf16(x) against lo(W)); with the TF32 hi*hi MMA that is 2 instead of 3 tensor-pipe instructions per
 // product.  The cross terms are 2^-12 of the product, so bf16's 2^-9 rounding leaves an error of ~2^-21 per product.
 // PDL_CROSS_BF16 is a bit mask: 1 = forward, 2 = data gradient, 4 = weight gradient.
-constexpr bool XBF_F = (PDL_CROSS_BF16 & 1) != 0, XBF_D = (PDL_CROSS_BF16 & 2) != 0, XBF_W = (PDL_CROSS_BF16 & 4) != 0;
+// bit 8: the forward cross terms as ONE scaled fp16 m16n8k16 MMA (11-bit significands: error at the 3xTF32 level, see split_cross_f16);
+// it uses the same packed cross plane of W as bit 1, so XBF_F ("forward cross terms in one 16-bit MMA") covers both
+constexpr bool XF16_F = (PDL_CROSS_BF16 & 8) != 0;
+constexpr bool XBF_F = (PDL_CROSS_BF16 & 1) != 0 || XF16_F, XBF_D = (PDL_CROSS_BF16 & 2) != 0, XBF_W = (PDL_CROSS_BF16 & 4) != 0;
 constexpr bool WGRAD_MMA = (PDL_WGRAD_MMA != 0);   // weight gradient on the tensor pipe (k = the tile's 8 points, one k-step per component)
 constexpr int NMT = (WP + 15) / 16;         // m16 tiles over the output neurons of a weight-gradient block
 constexpr int NFRAG = NMT * NT8;            // C fragments of one layer's weight gradient
@@ -146,6 +149,85 @@ PDL_DEV void split_cross(float v0, float v1, float v2, float v3, uint32_t (&hi)[
     x[1] = pack_bf16(v1 - u2f(hi[1]), v3 - u2f(hi[3]));
     x[2] = pack_bf16(v0, v2);
     x[3] = pack_bf16(v1, v3);
+}
+// ---- scaled fp16 cross terms (forward pass) ----
+// fp16 has the 11-bit significand the cross terms need (bf16's 8 bits leave 1.4e-5 on the derivative features) but only 5 exponent
+// bits.  The two products of the cross MMA are scaled apart by exact powers of two:  slots 0-7  (lo(x) * 2^11) * (W * 2^-11),
+// slots 8-15  x * lo(W).  lo(x) * 2^11 ~ x/2 is a normal fp16 for |x| > 2^-13; W * 2^-11 is normal for |W| >= 1/8 and subnormal below
+// (absolute error 2^-25, i.e. 2^-14 in W): the term lo(x) * W then carries an error of |x| * 2^-26 -- below FP32's own rounding of the
+// sum.  x and lo(W) in the other product are rounded to 11 bits (or, tiny, to fp16 subnormals: absolute 2^-25), which changes a
+// term of size 2^-12 |x W| by 2^-23 |x W| at most.  Conversions saturate (.satfinite): |x| > 65504 degrades to TF32 accuracy
+// instead of producing inf.
+constexpr float F16_UP = 2048.f, F16_DOWN = 1.f / 2048.f;
+#ifdef PDL_EMULATE
+PDL_DEV uint32_t f32_to_f16_bits(float f) {            // round to nearest even, subnormals, saturating
+    uint32_t x = f2u(f);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    x &= 0x7FFFFFFFu;
+    if (x > 0x7F800000u) return sign | 0x7E00u;                          // NaN
+    if (x >= 0x477FF000u) return sign | 0x7BFFu;                         // >= 65520 (rounds past the largest finite): saturate
+    if (x < 0x33000001u) return sign;                                    // < 2^-25 (or exactly 2^-25: ties to even = 0)
+    const int e = (int)(x >> 23) - 127;
+    uint32_t m = (x & 0x7FFFFFu) | 0x800000u;
+    int shift = (e >= -14) ? 13 : (13 + (-14 - e));                      // bits dropped from the 24-bit significand
+    const uint32_t half = 1u << (shift - 1), rem = m & ((1u << shift) - 1u);
+    uint32_t q = m >> shift;
+    if (rem > half || (rem == half && (q & 1u))) ++q;
+    uint32_t out = (e >= -14) ? ((uint32_t)(e + 15) << 10) + (q - 0x400u) : q;   // a carry out of the significand bumps the exponent
+    return sign | out;
+}
+PDL_DEV float f16_bits_to_f32(uint32_t h) {
+    const uint32_t sign = (h & 0x8000u) << 16, e = (h >> 10) & 0x1Fu, m = h & 0x3FFu;
+    if (e == 0) { const float v = (float)m * 5.9604644775390625e-08f; return u2f(f2u(v) | sign); }
+    if (e == 31) return u2f(sign | 0x7F800000u | (m << 13));
+    return u2f(sign | ((e + 112u) << 23) | (m << 13));
+}
+#endif
+// two FP32 values -> packed f16x2, round to nearest even, saturating; `k0` lands in the low half
+PDL_DEV uint32_t pack_f16(float k0, float k1) {
+#ifdef PDL_EMULATE
+    return (f32_to_f16_bits(k1) << 16) | (f32_to_f16_bits(k0) & 0xFFFFu);
+#else
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(k1), "f"(k0));
+    return r;
+#endif
+}
+// A-operand registers of one component pair: hi[] = TF32 fragment, x[] = scaled fp16 cross fragment (layout as split_cross)
+PDL_DEV void split_cross_f16(float v0, float v1, float v2, float v3, uint32_t (&hi)[4], uint32_t (&x)[4]) {
+    hi[0] = tf32_rna(v0); hi[1] = tf32_rna(v1); hi[2] = tf32_rna(v2); hi[3] = tf32_rna(v3);
+    x[0] = pack_f16((v0 - u2f(hi[0])) * F16_UP, (v2 - u2f(hi[2])) * F16_UP);
+    x[1] = pack_f16((v1 - u2f(hi[1])) * F16_UP, (v3 - u2f(hi[3])) * F16_UP);
+    x[2] = pack_f16(v0, v2);
+    x[3] = pack_f16(v1, v3);
+}
+// the same MMA shape with fp16 inputs
+PDL_DEV void warp_mma_f16(float (&d)[PDL_NL][4], const uint32_t (&a)[PDL_NL][4], const uint32_t (&b)[PDL_NL][2]) {
+#ifdef PDL_EMULATE
+    float A[16][16], B[16][8];
+    for (int l = 0; l < 32; ++l) {
+        const int g = l >> 2, t = l & 3;
+        for (int e = 0; e < 2; ++e) {
+            const int sh = 16 * e;
+            A[g][2 * t + e] = f16_bits_to_f32((a[l][0] >> sh) & 0xFFFFu); A[g + 8][2 * t + e] = f16_bits_to_f32((a[l][1] >> sh) & 0xFFFFu);
+            A[g][2 * t + 8 + e] = f16_bits_to_f32((a[l][2] >> sh) & 0xFFFFu); A[g + 8][2 * t + 8 + e] = f16_bits_to_f32((a[l][3] >> sh) & 0xFFFFu);
+            B[2 * t + e][g] = f16_bits_to_f32((b[l][0] >> sh) & 0xFFFFu); B[2 * t + 8 + e][g] = f16_bits_to_f32((b[l][1] >> sh) & 0xFFFFu);
+        }
+    }
+    for (int l = 0; l < 32; ++l) {
+        const int g = l >> 2, t = l & 3;
+        for (int q = 0; q < 4; ++q) {
+            const int r = g + ((q & 2) ? 8 : 0), c = 2 * t + (q & 1);
+            float s = d[l][q];
+            for (int k = 0; k < 16; ++k) s += A[r][k] * B[k][c];
+            d[l][q] = s;
+        }
+    }
+#else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0][0]), "+f"(d[0][1]), "+f"(d[0][2]), "+f"(d[0][3])
+                 : "r"(a[0][0]), "r"(a[0][1]), "r"(a[0][2]), "r"(a[0][3]), "r"(b[0][0]), "r"(b[0][1]));
+#endif
 }
 // D(16x8) += A(16x16) * B(16x8), bf16 inputs, FP32 accumulate (mma.sync.m16n8k16).  lane = 4g + t:
 //   A: a0 (g; k = 2t, 2t+1)  a1 (g+8; 2t, 2t+1)  a2 (g; 2t+8, 2t+9)  a3 (g+8; 2t+8, 2t+9);  B: b0 (k = 2t, 2t+1; n = g)  b1 (k = 2t+8, 2t+9; n = g)
@@ -281,8 +363,13 @@ PDL_DEV void stage_thread2(const Params& P, float* sm, int tid) {
             if (!XBF_F) base[HH_WLO + n * SF + k] = u2f(ul);
             else if ((k & 1) == 0) {                                       // packed bf16 cross operands of the pair (k, k+1)
                 const float w1 = (k + 1 < win) ? W[e + 1] : 0.f;
-                base[HH_WLO + n * SF + k] = u2f(pack_bf16(w, w1));
-                base[HH_WLO + n * SF + k + 1] = u2f(pack_bf16(w - u2f(uh), w1 - u2f(tf32_rna(w1))));
+                if (XF16_F) {
+                    base[HH_WLO + n * SF + k] = u2f(pack_f16(w * F16_DOWN, w1 * F16_DOWN));
+                    base[HH_WLO + n * SF + k + 1] = u2f(pack_f16(w - u2f(uh), w1 - u2f(tf32_rna(w1))));
+                } else {
+                    base[HH_WLO + n * SF + k] = u2f(pack_bf16(w, w1));
+                    base[HH_WLO + n * SF + k + 1] = u2f(pack_bf16(w - u2f(uh), w1 - u2f(tf32_rna(w1))));
+                }
             }
             if (DGRAD_T) base[HH_THI + k * SF + n] = u2f(uh);
             if (DGRAD_T && !XBF_D) base[HH_TLO + k * SF + n] = u2f(ul);
@@ -399,7 +486,8 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                         const float v0 = h[PDL_L][2 * s][2 * m], v2 = h[PDL_L][2 * s + 1][2 * m];
                         const float v1 = (2 * m + 1 < J) ? h[PDL_L][2 * s][(2 * m + 1 < J) ? 2 * m + 1 : 0] : 0.f;
                         const float v3 = (2 * m + 1 < J) ? h[PDL_L][2 * s + 1][(2 * m + 1 < J) ? 2 * m + 1 : 0] : 0.f;
-                        if (XBF_F) split_cross(v0, v1, v2, v3, ahi[m][PDL_L], alo[m][PDL_L]);
+                        if (XF16_F) split_cross_f16(v0, v1, v2, v3, ahi[m][PDL_L], alo[m][PDL_L]);
+                        else if (XBF_F) split_cross(v0, v1, v2, v3, ahi[m][PDL_L], alo[m][PDL_L]);
                         else {
                             split_tf32(v0, ahi[m][PDL_L][0], alo[m][PDL_L][0]);
                             split_tf32(v1, ahi[m][PDL_L][1], alo[m][PDL_L][1]);
@@ -421,7 +509,7 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
 #pragma unroll
                         for (int m = 0; m < NM; ++m) warp_mma(accf[q][m], ahi[m], bhi);
 #pragma unroll
-                        for (int m = 0; m < NM; ++m) warp_mma_bf16(accf[q][m], alo[m], blo);
+                        for (int m = 0; m < NM; ++m) { if (XF16_F) warp_mma_f16(accf[q][m], alo[m], blo); else warp_mma_bf16(accf[q][m], alo[m], blo); }
                     } else {
 #pragma unroll
                         for (int m = 0; m < NM; ++m) {

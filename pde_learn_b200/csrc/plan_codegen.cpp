@@ -253,12 +253,12 @@ std::string generate_plan_source(const PlanSpec& spec, PlanMeta* meta_out) {
         // cross terms hi*lo + lo*hi of the split products as ONE bf16 m16n8k16 MMA (2 tensor-pipe instructions per product instead of
         // 3); bit mask: 1 = forward, 2 = data gradient, 4 = weight gradient.  Default 6: measured 8-11 % faster with unchanged parity
         // errors; the forward (bit 1) would gain another 3-7 % but its errors reach 1.4e-5 on the derivative features (gate: 1e-5).
-        meta.cross_bf16 = (spec.cross_bf16 >= 0) ? (spec.cross_bf16 & 7) : 6;
+        meta.cross_bf16 = (spec.cross_bf16 >= 0) ? (spec.cross_bf16 & 15) : 6;      // bit 8: forward cross terms as scaled fp16
         if (!meta.dgrad_mma) meta.cross_bf16 &= ~2;
         if (!meta.wgrad_mma) meta.cross_bf16 &= ~4;
         // mode 2 reads the TF32 lo plane of W that the bf16 forward replaces: forward bf16 then needs the data gradient bf16 as well
-        if (meta.dgrad_mma == 2 && (meta.cross_bf16 & 1)) meta.cross_bf16 |= 2;
-        if (meta.dgrad_mma == 2 && (meta.cross_bf16 & 2) && smem_floats(meta, nw) * 4 > 227 * 1024) meta.cross_bf16 &= ~3;
+        if (meta.dgrad_mma == 2 && (meta.cross_bf16 & 9)) meta.cross_bf16 |= 2;
+        if (meta.dgrad_mma == 2 && (meta.cross_bf16 & 2) && smem_floats(meta, nw) * 4 > 227 * 1024) meta.cross_bf16 &= ~11;
     }
     // launches without gradients on the tcgen05 / TMEM forward engine (jet_mlp_fwd_tc.cuh) when the jet set fits the 512 tensor-memory
     // columns: two accumulator sets (J components at a pitch of NP, or WP with overlapping padding columns) + one or two ring slots,
