@@ -401,7 +401,7 @@ def run_ours(args):
         if "jet_mlp_kernel_mma.cuh" in src:
             nt8, nm, nmt = df["PDL_WP"] // 8, (df["PDL_J"] + 1) // 2, (df["PDL_WP"] + 15) // 16
             xb = df.get("PDL_CROSS_BF16", 0)
-            per_prod = {"forward": 2 if xb & 1 else 3, "dgrad": 2 if xb & 2 else 3, "wgrad": 2 if xb & 4 else 3}
+            per_prod = {"forward": 2 if xb & 9 else 3, "dgrad": 2 if xb & 2 else 3, "wgrad": 2 if xb & 4 else 3}
             per_layer = (per_prod["forward"] * nt8 * nt8 * nm + (per_prod["dgrad"] * nt8 * nt8 * nm if df["PDL_DGRAD_MMA"] else 0) +
                          (per_prod["wgrad"] * nmt * nt8 * df["PDL_J"] if df["PDL_WGRAD_MMA"] else 0))
             mma_flops_pt = per_layer * (df["PDL_H"] - 1) * (16 * 8 * 8 * 2) / 8.0
@@ -414,7 +414,7 @@ def run_ours(args):
                                                                       (["wgrad"] if df["PDL_WGRAD_MMA"] else []),
                                        "peak_source": "mma.sync.m16n8k8 TF32 microbenchmark, profiles/r01_ubench.txt (277 TFLOP/s = "
                                                       "1.35e11 MMA instructions/s; bf16 m16n8k16 issues at the same rate); split "
-                                                      "products (3 MMAs, or TF32 hi*hi + one bf16 cross-term MMA) and padding are "
+                                                      "products (TF32 hi*hi + one 16-bit cross-term MMA: scaled fp16 forward, bf16 adjoint) and padding are "
                                                       "executed, not algorithmic, work; executed_tflops counts 2048 flop per MMA"}
     except Exception as ex:                                                  # informational only
         roofline["tensor_pipe"] = {"error": str(ex)}

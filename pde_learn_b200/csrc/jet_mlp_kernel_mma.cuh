@@ -2,9 +2,11 @@
 //
 // Same contract, tiling (8 points per warp tile), scratch, reductions and helpers as jet_mlp_kernel.cuh (see there for the
 // reference map).  The contractions whose A operand is produced by the lane itself -- forward  z = W h  and, optionally, the
-// data gradient  hb = zb W  -- run as 3xTF32 mma.sync.m16n8k8 on the tensor pipe, concurrently with the FP32 pipe that keeps
-// the jet activations and the epilogue (and the weight gradient unless PDL_WGRAD_MMA moves it to the tensor pipe as well).  FP32-class accuracy comes from the split x = hi + lo
-// (hi = TF32(x), lo = TF32(x - hi)):  D += lo*Bhi + hi*Blo + hi*Bhi.
+// data gradient  hb = zb W  -- run as split-precision mma.sync on the tensor pipe, concurrently with the FP32 pipe that keeps
+// the jet activations and the epilogue (and the weight gradient unless PDL_WGRAD_MMA moves it to the tensor pipe as well).
+// FP32-class accuracy comes from the split x = hi + lo (hi = TF32(x), lo = x - hi):  D += hi*Bhi (TF32 m16n8k8) + the two cross
+// terms lo*B + hi*Blo either as two more TF32 MMAs (3xTF32) or as ONE 16-bit m16n8k16 MMA (PDL_CROSS_BF16 bit mask: scaled fp16 in
+// the forward pass, bf16 in the adjoint: the defaults).
 //
 // Included at the END of a generated plan translation unit when the plan compiler picks this engine (PDL_ENGINE=mma).
 // The same source compiles as plain C++ with -DPDL_EMULATE (mma.sync is modelled lane-exactly): TEST INFRASTRUCTURE only.

@@ -253,7 +253,10 @@ std::string generate_plan_source(const PlanSpec& spec, PlanMeta* meta_out) {
         // cross terms hi*lo + lo*hi of the split products as ONE bf16 m16n8k16 MMA (2 tensor-pipe instructions per product instead of
         // 3); bit mask: 1 = forward, 2 = data gradient, 4 = weight gradient.  Default 6: measured 8-11 % faster with unchanged parity
         // errors; the forward (bit 1) would gain another 3-7 % but its errors reach 1.4e-5 on the derivative features (gate: 1e-5).
-        meta.cross_bf16 = (spec.cross_bf16 >= 0) ? (spec.cross_bf16 & 15) : 6;      // bit 8: forward cross terms as scaled fp16
+        // default 14 = data + weight gradient cross terms as one bf16 MMA (bits 2, 4) and the forward cross terms as one SCALED fp16 MMA
+        // (bit 8: 11-bit significands; measured on B200 -2.6 ... -6.8 % kernel time with parity errors equal or smaller than 3xTF32,
+        // profiles/r02_ab_fp16_forward.txt).  Bit 1 (forward cross terms in bf16) stays an opt-in the parity gate rejects (1.4e-5).
+        meta.cross_bf16 = (spec.cross_bf16 >= 0) ? (spec.cross_bf16 & 15) : 14;
         if (!meta.dgrad_mma) meta.cross_bf16 &= ~2;
         if (!meta.wgrad_mma) meta.cross_bf16 &= ~4;
         // mode 2 reads the TF32 lo plane of W that the bf16 forward replaces: forward bf16 then needs the data gradient bf16 as well

@@ -17,5 +17,6 @@ CASES = [
 ]
 
 # (environment knobs, tolerance) of tests/test_gpu_parity.py::test_tensor_pipe_kernel_variants_subprocess
-KERNEL_VARIANTS = [({"PDL_CROSS_BF16": "0"}, 1e-5), ({"PDL_ADJ_FUSED": "1"}, 1e-5), ({"PDL_ADJ_FUSED": "0"}, 1e-5),
+# (default = 14: scaled fp16 forward cross terms + bf16 adjoint cross terms; 6 = the round-1 default with a 3xTF32 forward)
+KERNEL_VARIANTS = [({"PDL_CROSS_BF16": "0"}, 1e-5), ({"PDL_CROSS_BF16": "6"}, 1e-5), ({"PDL_ADJ_FUSED": "1"}, 1e-5), ({"PDL_ADJ_FUSED": "0"}, 1e-5),
                    ({"PDL_CROSS_BF16": "7"}, 3e-5)]
