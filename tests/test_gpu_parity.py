@@ -315,7 +315,9 @@ def test_tcgen05_forward_engine_vs_mma_forward_and_oracle(workload, act):
         torch.cuda.synchronize()
         scale = float(r_b.abs().max())
         assert float((r_f - r_b).abs().max()) <= TOL * scale, (B, float((r_f - r_b).abs().max()) / scale)
-        assert abs(float(st_f[0]) - float(st_b[0])) <= TOL * abs(float(st_b[0])), B
+        # the loss is quadratic in the residual: two engines that are each within TOL of the truth in r can differ by 2 TOL in r^2
+        # (it shows at B = 1, where the "max-norm" of the residual is the one residual itself)
+        assert abs(float(st_f[0]) - float(st_b[0])) <= 2.5 * TOL * abs(float(st_b[0])), B
         assert abs(float(st_f[2]) - float(st_b[2])) <= TOL * abs(float(st_b[2])), B          # sum |r| (targeted-point moments)
     # features of the last (largest) launch against the float64 oracle on a subset of its rows
     n = 400
