@@ -289,10 +289,12 @@ std::string generate_plan_source(const PlanSpec& spec, PlanMeta* meta_out) {
       << "\n#define PDL_NW " << nw << "\n#define PDL_MODE " << spec.mode << "\n#define PDL_SF " << meta.sf
       << "\n#define PDL_GS " << meta.gs << "\n#define PDL_DGRAD_MMA " << meta.dgrad_mma
       << "\n#define PDL_WGRAD_MMA " << meta.wgrad_mma << "\n#define PDL_CROSS_BF16 " << meta.cross_bf16
-      << "\n#define PDL_ADJ_FUSED " << meta.adj_fused << "\n#define PDL_WGRAD_ROLL_MT " << ((J >= 5 || meta.adj_fused) ? 1 : 0)
+      << "\n#define PDL_ADJ_FUSED " << meta.adj_fused
+      // (#ifndef: A/B runs override these two with PDL_NVCC_FLAGS=-D...)
+      << "\n#ifndef PDL_WGRAD_ROLL_MT\n#define PDL_WGRAD_ROLL_MT " << ((J >= 5 || meta.adj_fused) ? 1 : 0) << "\n#endif"
       // tanh(z0) cached in a register per neuron for the next adjoint: +1-2 % with the fused order (kdv 4.19 -> 4.09 ms), -4 % for
       // the classic-order J <= 4 kernels (heat 3.03 -> 3.16 ms: spills)
-      << "\n#define PDL_TANH_CACHE " << ((spec.activation == 0 && meta.adj_fused) ? 1 : 0) << "\n";
+      << "\n#ifndef PDL_TANH_CACHE\n#define PDL_TANH_CACHE " << ((spec.activation == 0 && meta.adj_fused) ? 1 : 0) << "\n#endif\n";
     // n8 tiles per weight-gradient step: 3 everywhere except the classic-order tanh kernels (heat), which the round-2 sweep with the
     // fp16 forward in place puts at 2 (2.915 vs 3.010 ms; Rational and J = 6 lose 1-5 % with 2: profiles/r02_knob_sweep.txt)
     if (meta.engine == 1 && spec.activation == 0 && !meta.adj_fused) o << "#ifndef PDL_WGRAD_NTB\n#define PDL_WGRAD_NTB 2\n#endif\n";
