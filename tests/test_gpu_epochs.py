@@ -221,3 +221,23 @@ def test_settings_driver_end_to_end(optimizer, graph, tmp_path):
     if optimizer == "Adam":
         blob = torch.load(str(root / "Saves" / r2["Save Name"]), weights_only=False)
         assert float(blob["Optimizer"]["state"][0]["step"]) == 2 * epochs
+
+
+def test_three_stage_workflow_recovers_burgers_pde():
+    """The deliverable end to end (README.md:90-94 of the reference): burn-in -> sparsification -> fine-tuning through the Settings.txt
+    driver with captured epochs, on the data-set file and the three Settings files the unmodified reference's main.py ran
+    (tests/golden/make_reference_workflow.py).  Same thresholded support as the reference's own run = the true PDE
+    u_t = -u u_x + 0.1 u_xx (Burgers_Sine.m:20-21), coefficients within 15 % of the truth (the reference: -0.963, 0.1022)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "gpurun_out", "test_staged_workflow.json")
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "staged_workflow.py"), "--out", out], capture_output=True, text=True,
+                       timeout=900, cwd=root)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    res = json.load(open(out))
+    assert res["same_support_as_reference"] and res["recovered_true_support"]
+    last = res["stages"][-1]
+    assert last["support"] == [2, 5]
+    assert abs(last["xi"][5] + 1.0) <= 0.15 and abs(last["xi"][2] - 0.1) <= 0.015
+    assert last["seconds_per_epoch"] < 0.01                                     # the reference: 0.24 s per epoch on 8 host cores
