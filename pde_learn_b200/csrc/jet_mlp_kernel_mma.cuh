@@ -404,6 +404,19 @@ PDL_DEV void stage_thread2(const Params& P, float* sm, int tid) {
     }
 }
 
+// running per-warp partial sum of a weight-gradient fragment in the warp's private global buffer: load + rounded add + store, or
+// (PDL_WGRAD_RED, an A/B knob) one fire-and-forget vector reduction at the L2 -- the buffer is private to the warp and a thread's
+// reductions to one address are performed in program order, so the sum is the same sequence of rounded additions either way
+#ifndef PDL_WGRAD_RED
+#define PDL_WGRAD_RED 0
+#endif
+#if !defined(PDL_EMULATE) && PDL_WGRAD_RED
+PDL_DEV void red4(float* q, pdl_f4 r, bool first) {
+    if (first) { stg4(q, r); return; }
+    asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(r.x), "f"(r.y), "f"(r.z), "f"(r.w) : "memory");
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // the per-warp tile loop
 // ---------------------------------------------------------------------------------------------
@@ -772,8 +785,12 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                                         r.z = (c4[b][0][PDL_L][2] + c4[b][1][PDL_L][2]) + c4[b][NACW - 1][PDL_L][2];
                                         r.w = (c4[b][0][PDL_L][3] + c4[b][1][PDL_L][3]) + c4[b][NACW - 1][PDL_L][3];
                                     }
+#if !defined(PDL_EMULATE) && PDL_WGRAD_RED
+                                    red4(q, r, first);
+#else
                                     if (!first) { const pdl_f4 o = ldg4(q); r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
                                     stg4(q, r);
+#endif
                                 }
                             }
                         }
@@ -782,8 +799,12 @@ PDL_DEV void warp_body(const Params& P, float* sm, int warp_in_cta, int gwarp, i
                 PDL_FOR_LANES {                                            // bias slot: lane (g, t) owns neurons 16t+g and 16t+g+8
                     float* q = wpl + (NFRAG * 32 + lane) * 4;
                     pdl_f4 r; r.x = bsel[PDL_L][0]; r.y = bsel[PDL_L][1]; r.z = 0.f; r.w = 0.f;
+#if !defined(PDL_EMULATE) && PDL_WGRAD_RED
+                    red4(q, r, first);
+#else
                     if (!first) { const pdl_f4 o = ldg4(q); r.x += o.x; r.y += o.y; }
                     stg4(q, r);
+#endif
                 }
             }
         };
