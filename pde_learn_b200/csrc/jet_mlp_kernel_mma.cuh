@@ -404,11 +404,14 @@ PDL_DEV void stage_thread2(const Params& P, float* sm, int tid) {
     }
 }
 
-// running per-warp partial sum of a weight-gradient fragment in the warp's private global buffer: load + rounded add + store, or
-// (PDL_WGRAD_RED, an A/B knob) one fire-and-forget vector reduction at the L2 -- the buffer is private to the warp and a thread's
-// reductions to one address are performed in program order, so the sum is the same sequence of rounded additions either way
+// running per-warp partial sum of a weight-gradient fragment in the warp's private global buffer: ONE fire-and-forget vector reduction
+// at the L2 (red.global.v4.f32.add) per fragment and tile instead of load + rounded add + store.  The buffer is private to the warp and
+// a thread's reductions to one address are performed in program order, so the sum is the same sequence of rounded additions (launches
+// stay bit-identical: tested) -- but the kernel no longer waits for 32 KB of partial sums per tile to come back from the L2 and holds
+// 19 registers less (heat: 255 with 44 B of spills -> 236, none).  B200, 2^20 rows (profiles/r02_ab_wgrad_red.txt): heat 2.95 -> 2.80 ms,
+// KdV 3.82 -> 3.71, KS 4.68 -> 4.58, rd2d 4.11 -> 4.00, heat Rational 3.37 -> 3.29, KS Rational unchanged.  PDL_WGRAD_RED=0: the old form.
 #ifndef PDL_WGRAD_RED
-#define PDL_WGRAD_RED 0
+#define PDL_WGRAD_RED 1
 #endif
 #if !defined(PDL_EMULATE) && PDL_WGRAD_RED
 PDL_DEV void red4(float* q, pdl_f4 r, bool first) {
