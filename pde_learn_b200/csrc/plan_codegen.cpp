@@ -295,12 +295,11 @@ std::string generate_plan_source(const PlanSpec& spec, PlanMeta* meta_out) {
       // tanh(z0) cached in a register per neuron for the next adjoint: +1-2 % with the fused order (kdv 4.19 -> 4.09 ms), -4 % for
       // the classic-order J <= 4 kernels (heat 3.03 -> 3.16 ms: spills)
       << "\n#ifndef PDL_TANH_CACHE\n#define PDL_TANH_CACHE " << ((spec.activation == 0 && meta.adj_fused) ? 1 : 0) << "\n#endif\n";
-    // n8 tiles per weight-gradient step: 3 everywhere except the classic-order tanh kernels (heat), which the round-2 sweep with the
-    // fp16 forward in place puts at 2 (2.915 vs 3.010 ms; Rational and J = 6 lose 1-5 % with 2: profiles/r02_knob_sweep.txt)
-    // (second and third sweep: tanh J = 5 -- Burgers, KdV -- prefers all 5 tiles in one step, 3.95 -> 3.83 ms; Rational J = 5 and
-    // everything at J = 6 stay at 3: profiles/r02_knob_sweep2.txt, r02_knob_sweep3.txt)
-    if (meta.engine == 1 && spec.activation == 0 && !meta.adj_fused) o << "#ifndef PDL_WGRAD_NTB\n#define PDL_WGRAD_NTB 2\n#endif\n";
-    else if (meta.engine == 1 && spec.activation == 0 && J == 5 && WP == 40) o << "#ifndef PDL_WGRAD_NTB\n#define PDL_WGRAD_NTB 5\n#endif\n";
+    // n8 tiles per weight-gradient step (independent MMA chains vs registers).  3 since round 1; re-swept in round 2 after the fp16 forward
+    // and the L2-reduction flush changed the register picture (profiles/r02_knob_sweep{,2,3,4,5}.txt, A-B-A on one box): all 5 tiles of
+    // a 40-wide layer in one step for tanh plans with J <= 5 (heat 2.80 -> 2.70 ms, Burgers / KdV 3.95 -> 3.83) and for Rational J = 5
+    // (KdV 4.47 -> 4.42); J = 6 (KS, rd2d) loses 2.5-3.5 % with 5 and Rational J = 4 is indifferent: they keep 3.
+    if (meta.engine == 1 && WP == 40 && ((spec.activation == 0 && J <= 5) || J == 5)) o << "#ifndef PDL_WGRAD_NTB\n#define PDL_WGRAD_NTB 5\n#endif\n";
     o << "#ifdef PDL_EMULATE\n#define PDL_GEN static inline\n#else\n#define PDL_GEN __host__ __device__ __forceinline__\n#endif\n";
 
     // widths / first-order component -> axis
